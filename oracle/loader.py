@@ -1,0 +1,240 @@
+"""oracle/loader.py -- TEST INFRASTRUCTURE: ctypes bindings of the two CPU checkers.
+
+* ``port()``  -> oracle/_build/liboracle.so : the plain-C restatement (oracle.c / oracle_body.h).
+* ``ref()``   -> oracle/_ref/libeigen_ref_v{4,3}.so : the unmodified reference (Eigen) compiled from
+  /root/reference by oracle/Makefile in the build container; travels prebuilt to the GPU box.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import this module.  The product package
+(eigen-git-mirror_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LOWER, UPPER, BOTH = 1, 2, 3
+IDENTITY, JACOBI = 0, 1
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+
+
+def _cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def host_lanes(dtype=np.float64) -> int:
+    """Packet width (in scalars) that the loaded oracle/_ref variant reduces with."""
+    v4 = {"avx512f", "avx512dq", "avx512vl", "avx512bw", "avx512cd"} <= _cpu_flags()
+    doubles = 8 if v4 else 4
+    return doubles * (2 if np.dtype(dtype) == np.float32 else 1)
+
+
+def build_port():
+    subprocess.run(["make", "-C", HERE, "port"], check=True, capture_output=True)
+
+
+def build_ref(reference="/root/reference"):
+    """Build oracle/_ref from the reference sources where they lie; no-op when they are absent (GPU box)."""
+    if os.path.isdir(os.path.join(reference, "Eigen")):
+        subprocess.run(["make", "-C", HERE, "ref", f"REF={reference}"], check=True, capture_output=True)
+        return True
+    return False
+
+
+class Port:
+    def __init__(self):
+        path = os.path.join(HERE, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            build_port()
+        self.lib = L = C.CDLL(path)
+        for sfx, fp, real in (("f64", _f64p, C.c_double), ("f32", _f32p, C.c_float)):
+            getattr(L, f"oracle_spmv_{sfx}").argtypes = [C.c_int64, _i32p, _i32p, fp, fp, fp]
+            getattr(L, f"oracle_spmv_{sfx}").restype = None
+            getattr(L, f"oracle_spmv_blk_{sfx}").argtypes = [C.c_int64, _i32p, _i32p, fp, fp, fp, C.c_int]
+            getattr(L, f"oracle_spmv_blk_{sfx}").restype = None
+            getattr(L, f"oracle_symv_{sfx}").argtypes = [C.c_int64, _i32p, _i32p, fp, fp, fp, C.c_int]
+            getattr(L, f"oracle_symv_{sfx}").restype = None
+            getattr(L, f"oracle_jacobi_factorize_{sfx}").argtypes = [C.c_int64, _i32p, _i32p, fp, fp]
+            getattr(L, f"oracle_jacobi_factorize_{sfx}").restype = None
+            getattr(L, f"oracle_dot_{sfx}").argtypes = [fp, fp, C.c_int64, C.c_int]
+            getattr(L, f"oracle_dot_{sfx}").restype = real
+            getattr(L, f"oracle_cg_{sfx}").argtypes = [C.c_int64, _i32p, _i32p, fp, fp, fp, real, C.c_int64, C.c_int,
+                                                      C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(real),
+                                                      C.POINTER(C.c_int)]
+            getattr(L, f"oracle_cg_{sfx}").restype = None
+            getattr(L, f"oracle_bicgstab_{sfx}").argtypes = [C.c_int64, _i32p, _i32p, fp, fp, fp, real, C.c_int64,
+                                                            C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(real),
+                                                            C.POINTER(C.c_int)]
+            getattr(L, f"oracle_bicgstab_{sfx}").restype = None
+        L.oracle_true_residual_f64.argtypes = [C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p]
+        L.oracle_true_residual_f64.restype = C.c_double
+
+    @staticmethod
+    def _sfx(a):
+        return "f32" if a.dtype == np.float32 else "f64"
+
+    def spmv(self, A, x, blk=None):
+        """blk: see oracle_spmv_blk; default = the pattern of the oracle/_ref variant this host loads
+        (0 for double; for float 8 on AVX-512 hosts, 4 otherwise)."""
+        if blk is None:
+            blk = 0 if A.vals.dtype == np.float64 else host_lanes(np.float32) // 2
+        y = np.empty(A.rows, dtype=A.vals.dtype)
+        getattr(self.lib, f"oracle_spmv_blk_{self._sfx(A.vals)}")(A.rows, A.rowptr, A.colidx, A.vals,
+                                                                 np.ascontiguousarray(x, A.vals.dtype), y, blk)
+        return y
+
+    def symv(self, A, x, uplo):
+        y = np.empty(A.rows, dtype=A.vals.dtype)
+        getattr(self.lib, f"oracle_symv_{self._sfx(A.vals)}")(A.rows, A.rowptr, A.colidx, A.vals,
+                                                             np.ascontiguousarray(x, A.vals.dtype), y, uplo)
+        return y
+
+    def jacobi(self, A):
+        d = np.empty(A.rows, dtype=A.vals.dtype)
+        getattr(self.lib, f"oracle_jacobi_factorize_{self._sfx(A.vals)}")(A.rows, A.rowptr, A.colidx, A.vals, d)
+        return d
+
+    def dot(self, a, b, lanes):
+        return getattr(self.lib, f"oracle_dot_{self._sfx(a)}")(a, b, a.shape[0], lanes)
+
+    def _solve(self, fn, A, b, x0, tol, max_iters, extra):
+        dt = A.vals.dtype
+        real = C.c_float if dt == np.float32 else C.c_double
+        x = np.zeros(A.rows, dt) if x0 is None else np.array(x0, dtype=dt, copy=True)
+        it, err, info = C.c_int64(0), real(0), C.c_int(0)
+        fn(A.rows, A.rowptr, A.colidx, A.vals, np.ascontiguousarray(b, dt), x, tol, max_iters, *extra,
+           C.byref(it), C.byref(err), C.byref(info))
+        return x, it.value, err.value, info.value
+
+    def cg(self, A, b, x0=None, tol=-1.0, max_iters=-1, uplo=BOTH, precond=JACOBI, lanes=None):
+        lanes = host_lanes(A.vals.dtype) if lanes is None else lanes
+        return self._solve(getattr(self.lib, f"oracle_cg_{self._sfx(A.vals)}"), A, b, x0, tol, max_iters,
+                           (uplo, precond, lanes))
+
+    def bicgstab(self, A, b, x0=None, tol=-1.0, max_iters=-1, precond=JACOBI, lanes=None):
+        lanes = host_lanes(A.vals.dtype) if lanes is None else lanes
+        return self._solve(getattr(self.lib, f"oracle_bicgstab_{self._sfx(A.vals)}"), A, b, x0, tol, max_iters,
+                           (precond, lanes))
+
+    def true_residual(self, A, x, b):
+        return self.lib.oracle_true_residual_f64(A.rows, A.rowptr, A.colidx, A.vals.astype(np.float64),
+                                                 np.ascontiguousarray(x, np.float64),
+                                                 np.ascontiguousarray(b, np.float64))
+
+
+class Ref:
+    """The unmodified reference (Eigen) behind oracle/ref_eigen.cpp."""
+
+    def __init__(self, variant=None):
+        if variant is None:
+            variant = "v4" if host_lanes() == 8 else "v3"
+        self.variant = variant
+        path = os.path.join(HERE, "_ref", f"libeigen_ref_{variant}.so")
+        if not os.path.exists(path):
+            if not build_ref() or not os.path.exists(path):
+                raise FileNotFoundError(f"{path}: build it with `make -C oracle ref` where /root/reference exists")
+        self.lib = L = C.CDLL(path)
+        L.eigref_max_threads.restype = C.c_int
+        L.eigref_build_info.restype = C.c_char_p
+        dp, ip64, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int)
+        for sfx, fp in (("f64", _f64p), ("f32", _f32p)):
+            getattr(L, f"eigref_spmv_{sfx}").argtypes = [C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, fp, fp, fp,
+                                                        C.c_int, C.c_int, dp]
+            getattr(L, f"eigref_cg_{sfx}").argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, fp, fp, fp, C.c_int,
+                                                      C.c_double, C.c_int64, C.c_int, C.c_int, C.c_int, ip64, dp, ip,
+                                                      dp, dp]
+            getattr(L, f"eigref_bicgstab_{sfx}").argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, fp, fp, fp, C.c_int,
+                                                            C.c_double, C.c_int64, C.c_int, C.c_int, ip64, dp, ip, dp,
+                                                            dp]
+        L.eigref_symv_f64.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int]
+        L.eigref_jacobi_f64.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p]
+
+    @property
+    def max_threads(self):
+        return self.lib.eigref_max_threads()
+
+    @property
+    def build_info(self):
+        return self.lib.eigref_build_info().decode()
+
+    @staticmethod
+    def _sfx(a):
+        return "f32" if a.dtype == np.float32 else "f64"
+
+    def spmv(self, A, x, threads=1, reps=1):
+        y = np.empty(A.rows, dtype=A.vals.dtype)
+        best = C.c_double(0)
+        rc = getattr(self.lib, f"eigref_spmv_{self._sfx(A.vals)}")(A.rows, A.cols, A.nnz, A.rowptr, A.colidx, A.vals,
+                                                                  np.ascontiguousarray(x, A.vals.dtype), y, threads,
+                                                                  reps, C.byref(best))
+        assert rc == 0
+        self.last_seconds = best.value
+        return y
+
+    def symv(self, A, x, uplo):
+        y = np.zeros(A.rows, dtype=np.float64)
+        assert self.lib.eigref_symv_f64(A.rows, A.nnz, A.rowptr, A.colidx, A.vals, x, y, uplo) == 0
+        return y
+
+    def jacobi_apply(self, A, r):
+        z = np.empty(A.rows, dtype=np.float64)
+        assert self.lib.eigref_jacobi_f64(A.rows, A.nnz, A.rowptr, A.colidx, A.vals, r, z) == 0
+        return z
+
+    def _solve(self, fn, A, b, x0, tol, max_iters, extra, threads):
+        dt = A.vals.dtype
+        x = np.zeros(A.rows, dt) if x0 is None else np.array(x0, dtype=dt, copy=True)
+        it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
+        ts, tv = C.c_double(0), C.c_double(0)
+        rc = fn(A.rows, A.nnz, A.rowptr, A.colidx, A.vals, np.ascontiguousarray(b, dt), x, int(x0 is not None),
+                tol, max_iters, *extra, threads, C.byref(it), C.byref(err), C.byref(info), C.byref(ts), C.byref(tv))
+        assert rc == 0
+        self.last_setup_seconds, self.last_solve_seconds = ts.value, tv.value
+        return x, it.value, err.value, info.value
+
+    def cg(self, A, b, x0=None, tol=-1.0, max_iters=-1, uplo=BOTH, precond=JACOBI, threads=1):
+        return self._solve(getattr(self.lib, f"eigref_cg_{self._sfx(A.vals)}"), A, b, x0, tol, max_iters,
+                           (uplo, precond), threads)
+
+    def bicgstab(self, A, b, x0=None, tol=-1.0, max_iters=-1, precond=JACOBI, threads=1):
+        return self._solve(getattr(self.lib, f"eigref_bicgstab_{self._sfx(A.vals)}"), A, b, x0, tol, max_iters,
+                           (precond,), threads)
+
+
+_port = None
+_ref = None
+
+
+def port() -> Port:
+    global _port
+    if _port is None:
+        _port = Port()
+    return _port
+
+
+def ref() -> Ref:
+    global _ref
+    if _ref is None:
+        _ref = Ref()
+    return _ref
+
+
+def ref_available() -> bool:
+    try:
+        ref()
+        return True
+    except (FileNotFoundError, OSError):
+        return False

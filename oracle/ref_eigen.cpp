@@ -1,0 +1,221 @@
+// oracle/ref_eigen.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Thin extern "C" wrapper around the UNMODIFIED reference (Eigen headers where they lie under
+// /root/reference), compiled by oracle/Makefile into oracle/_ref/libeigen_ref.so.  It contains no
+// algorithm of its own: every function instantiates the reference's own templates
+//   SparseMatrix<T,RowMajor,int> * Vector   Eigen/src/SparseCore/SparseDenseProduct.h:26-72
+//   ConjugateGradient<...>                   Eigen/src/IterativeLinearSolvers/ConjugateGradient.h:157-225
+//   BiCGSTAB<...>                            Eigen/src/IterativeLinearSolvers/BiCGSTAB.h:157-208
+//   DiagonalPreconditioner / Identity        Eigen/src/IterativeLinearSolvers/BasicPreconditioners.h:35-108,200-222
+// on caller-owned CSR arrays bound zero-copy through Map<const SparseMatrix> (SparseMap.h:270).
+//
+// Used for (1) pinning the C restatement in oracle/oracle.c, (2) generating tests/golden/*,
+// (3) the `--impl reference` arm and cpu_baseline of bench.py (kind "reference").
+// Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may load this library.
+#include <Eigen/Sparse>
+#include <Eigen/IterativeLinearSolvers>
+#include <chrono>
+#include <cstdint>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace Eigen;
+
+namespace {
+
+template <typename T>
+using Csr = SparseMatrix<T, RowMajor, int>;
+template <typename T>
+using CsrMap = Map<const Csr<T>>;
+template <typename T>
+using Vec = Matrix<T, Dynamic, 1>;
+
+inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+inline void set_threads(int threads) {
+  if (threads > 0) Eigen::setNbThreads(threads);
+}
+
+template <typename Solver, typename T>
+int run_solver(Solver& solver, const CsrMap<T>& A, int64_t n, const T* b, T* x, int use_guess, double tol,
+               int64_t max_iters, int64_t* iters, double* error, int* info, double* seconds_setup,
+               double* seconds_solve) {
+  Map<const Vec<T>> bm(b, n);
+  Map<Vec<T>> xm(x, n);
+  double t0 = now_s();
+  solver.compute(A);
+  double t1 = now_s();
+  if (tol >= 0) solver.setTolerance(static_cast<T>(tol));
+  if (max_iters >= 0) solver.setMaxIterations(max_iters);
+  Vec<T> sol;
+  double t2 = now_s();
+  if (use_guess) {
+    Vec<T> guess = xm;
+    sol = solver.solveWithGuess(bm, guess);
+  } else {
+    sol = solver.solve(bm);
+  }
+  double t3 = now_s();
+  xm = sol;
+  if (iters) *iters = solver.iterations();
+  if (error) *error = static_cast<double>(solver.error());
+  if (info) *info = static_cast<int>(solver.info());
+  if (seconds_setup) *seconds_setup = t1 - t0;
+  if (seconds_solve) *seconds_solve = t3 - t2;
+  return 0;
+}
+
+template <typename T>
+int cg_dispatch(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const T* vals, const T* b, T* x,
+                int use_guess, double tol, int64_t max_iters, int uplo, int precond, int threads, int64_t* iters,
+                double* error, int* info, double* t_setup, double* t_solve) {
+  set_threads(threads);
+  CsrMap<T> A(n, n, nnz, rowptr, colidx, vals);
+#define EIGREF_CG(UPLO, PRE)                                                                          \
+  {                                                                                                   \
+    ConjugateGradient<Csr<T>, UPLO, PRE> s;                                                           \
+    return run_solver(s, A, n, b, x, use_guess, tol, max_iters, iters, error, info, t_setup, t_solve); \
+  }
+  if (precond == 1) {
+    if (uplo == (Lower | Upper)) EIGREF_CG(Lower | Upper, DiagonalPreconditioner<T>)
+    if (uplo == Lower) EIGREF_CG(Lower, DiagonalPreconditioner<T>)
+    if (uplo == Upper) EIGREF_CG(Upper, DiagonalPreconditioner<T>)
+  } else if (precond == 0) {
+    if (uplo == (Lower | Upper)) EIGREF_CG(Lower | Upper, IdentityPreconditioner)
+    if (uplo == Lower) EIGREF_CG(Lower, IdentityPreconditioner)
+    if (uplo == Upper) EIGREF_CG(Upper, IdentityPreconditioner)
+  }
+#undef EIGREF_CG
+  return -1;
+}
+
+template <typename T>
+int bicgstab_dispatch(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const T* vals, const T* b,
+                      T* x, int use_guess, double tol, int64_t max_iters, int precond, int threads,
+                      int64_t* iters, double* error, int* info, double* t_setup, double* t_solve) {
+  set_threads(threads);
+  CsrMap<T> A(n, n, nnz, rowptr, colidx, vals);
+  if (precond == 1) {
+    BiCGSTAB<Csr<T>, DiagonalPreconditioner<T>> s;
+    return run_solver(s, A, n, b, x, use_guess, tol, max_iters, iters, error, info, t_setup, t_solve);
+  } else if (precond == 0) {
+    BiCGSTAB<Csr<T>, IdentityPreconditioner> s;
+    return run_solver(s, A, n, b, x, use_guess, tol, max_iters, iters, error, info, t_setup, t_solve);
+  }
+  return -1;
+}
+
+template <typename T>
+int spmv_impl(int64_t rows, int64_t cols, int64_t nnz, const int* rowptr, const int* colidx, const T* vals,
+              const T* x, T* y, int threads, int reps, double* best_seconds) {
+  set_threads(threads);
+  CsrMap<T> A(rows, cols, nnz, rowptr, colidx, vals);
+  Map<const Vec<T>> xm(x, cols);
+  Map<Vec<T>> ym(y, rows);
+  double best = 1e300;
+  for (int r = 0; r < (reps > 0 ? reps : 1); ++r) {
+    double t0 = now_s();
+    ym.noalias() = A * xm;  // the exact statement of ConjugateGradient.h:71
+    double t1 = now_s();
+    if (t1 - t0 < best) best = t1 - t0;
+  }
+  if (best_seconds) *best_seconds = best;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eigref_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+const char* eigref_build_info(void) {
+  return "Eigen " EIGEN_MAKESTRING(EIGEN_WORLD_VERSION) "." EIGEN_MAKESTRING(EIGEN_MAJOR_VERSION) "." EIGEN_MAKESTRING(
+      EIGEN_MINOR_VERSION) " g++ " __VERSION__
+#ifdef __AVX512F__
+                           " avx512"
+#elif defined(__AVX2__)
+                           " avx2"
+#else
+                           " sse2"
+#endif
+#ifdef __FMA__
+                           " fma"
+#endif
+#ifdef _OPENMP
+                           " openmp"
+#endif
+      ;
+}
+
+int eigref_spmv_f64(int64_t rows, int64_t cols, int64_t nnz, const int* rowptr, const int* colidx,
+                    const double* vals, const double* x, double* y, int threads, int reps, double* best_seconds) {
+  return spmv_impl<double>(rows, cols, nnz, rowptr, colidx, vals, x, y, threads, reps, best_seconds);
+}
+int eigref_spmv_f32(int64_t rows, int64_t cols, int64_t nnz, const int* rowptr, const int* colidx,
+                    const float* vals, const float* x, float* y, int threads, int reps, double* best_seconds) {
+  return spmv_impl<float>(rows, cols, nnz, rowptr, colidx, vals, x, y, threads, reps, best_seconds);
+}
+
+// y = selfadjointView<UpLo>(A) * x   (SparseSelfAdjointView.h:279-337); uplo 1=Lower 2=Upper
+int eigref_symv_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals,
+                    const double* x, double* y, int uplo) {
+  CsrMap<double> A(n, n, nnz, rowptr, colidx, vals);
+  Map<const Vec<double>> xm(x, n);
+  Map<Vec<double>> ym(y, n);
+  if (uplo == Lower)
+    ym.noalias() = A.selfadjointView<Lower>() * xm;
+  else if (uplo == Upper)
+    ym.noalias() = A.selfadjointView<Upper>() * xm;
+  else
+    return -1;
+  return 0;
+}
+
+int eigref_jacobi_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals,
+                      const double* r, double* z) {
+  CsrMap<double> A(n, n, nnz, rowptr, colidx, vals);
+  DiagonalPreconditioner<double> pre;
+  pre.compute(A);
+  Map<const Vec<double>> rm(r, n);
+  Map<Vec<double>> zm(z, n);
+  zm = pre.solve(rm);
+  return 0;
+}
+
+int eigref_cg_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals,
+                  const double* b, double* x, int use_guess, double tol, int64_t max_iters, int uplo, int precond,
+                  int threads, int64_t* iters, double* error, int* info, double* t_setup, double* t_solve) {
+  return cg_dispatch<double>(n, nnz, rowptr, colidx, vals, b, x, use_guess, tol, max_iters, uplo, precond,
+                             threads, iters, error, info, t_setup, t_solve);
+}
+int eigref_cg_f32(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const float* vals, const float* b,
+                  float* x, int use_guess, double tol, int64_t max_iters, int uplo, int precond, int threads,
+                  int64_t* iters, double* error, int* info, double* t_setup, double* t_solve) {
+  return cg_dispatch<float>(n, nnz, rowptr, colidx, vals, b, x, use_guess, tol, max_iters, uplo, precond, threads,
+                            iters, error, info, t_setup, t_solve);
+}
+int eigref_bicgstab_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals,
+                        const double* b, double* x, int use_guess, double tol, int64_t max_iters, int precond,
+                        int threads, int64_t* iters, double* error, int* info, double* t_setup,
+                        double* t_solve) {
+  return bicgstab_dispatch<double>(n, nnz, rowptr, colidx, vals, b, x, use_guess, tol, max_iters, precond,
+                                   threads, iters, error, info, t_setup, t_solve);
+}
+int eigref_bicgstab_f32(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const float* vals,
+                        const float* b, float* x, int use_guess, double tol, int64_t max_iters, int precond,
+                        int threads, int64_t* iters, double* error, int* info, double* t_setup, double* t_solve) {
+  return bicgstab_dispatch<float>(n, nnz, rowptr, colidx, vals, b, x, use_guess, tol, max_iters, precond, threads,
+                                  iters, error, info, t_setup, t_solve);
+}
+
+}  // extern "C"
