@@ -1,0 +1,21 @@
+"""eigen-git-mirror_b200 -- a B200-native (sm_100a) drop-in for ONE path of Eigen: CSR SpMV and the
+ConjugateGradient / BiCGSTAB loops with Jacobi or identity preconditioning.
+
+Layout
+  csrc/         hand-written CUDA kernels + the C ABI (include/b200sparse.h) -> lib/libb200sparse.so
+  solvers.py    host-side mirror of Eigen's solver interface over that C ABI (ctypes)
+  planning.py   GPU-free view of the partition / halo / tile plan (host logic, testable on CPU)
+  workloads.py  synthetic CSR matrices of BASELINE.json
+  build.py      nvcc build (in-tree)
+
+Importing the package does not load the CUDA library; the first solver / operator does, and raises if it is missing.
+"""
+from . import workloads  # noqa: F401
+from .solvers import (BiCGSTAB, Communicator, ConjugateGradient, DiagonalPreconditioner,  # noqa: F401
+                      IdentityPreconditioner, InvalidInput, Lower, NoConvergence, NumericalIssue, SparseOperator,
+                      Success, Upper, device_count, partition_rows)
+from ._lib import B200Error  # noqa: F401
+
+__all__ = ["ConjugateGradient", "BiCGSTAB", "SparseOperator", "Communicator", "partition_rows", "device_count",
+           "Lower", "Upper", "Success", "NumericalIssue", "NoConvergence", "InvalidInput", "DiagonalPreconditioner",
+           "IdentityPreconditioner", "B200Error", "workloads"]

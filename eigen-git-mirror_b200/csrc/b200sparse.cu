@@ -1,0 +1,1014 @@
+// b200sparse.cu -- C ABI (include/b200sparse.h) over the sm_100a kernels in kernels.cuh.
+//
+// Host-side structure of one handle (= one Eigen solver object, IterativeSolverBase.h:142-440):
+//   analyze_pattern : plan (plan.cpp) -> device pattern, tiles, peer window (multi-GPU), launch geometry
+//   factorize       : values -> device, Jacobi inverse diagonal (BasicPreconditioners.h:64-79)
+//   *_solve         : b/x0 -> device, ONE CUDA-graph launch whose WHILE node iterates until the device-resident
+//                     control state says stop, x -> host.  No host synchronisation inside the iteration.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sparse.h"
+#include "kernels.cuh"
+
+using namespace b200s;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct GraphSet {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t body_graph = nullptr;   // chunked mode: the unrolled body
+  cudaGraphExec_t body_exec = nullptr;
+  int init_kernels = 0, body_kernels = 0, tail_kernels = 0;
+  bool built = false;
+};
+
+}  // namespace
+
+struct b200s_handle {
+  b200s_config cfg{};
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  Plan plan;
+  bool analyzed = false, factorized = false;
+  int scalar_bytes = 0;  // 8 = f64, 4 = f32
+  int precond = B200S_PRECOND_JACOBI;
+  int loop_mode = B200S_LOOP_WHILE_GRAPH;
+  int spmv_impl = B200S_SPMV_STAGED;
+  int direct_lg = 0;
+  // device pattern / values
+  DevBuf rowptr, colidx, vals, src, tiles, invdiag, send_rows;
+  // vectors (doubles unless noted); ext = [owned | ghost]
+  DevBuf window;  // peer-visible: 4 extended slots + mailboxes + flags
+  size_t slot_bytes = 0, box_off = 0, flag_off = 0, halo_flag_off = 0, window_bytes = 0;
+  std::vector<void*> peer_window;  // [world], IPC-mapped (self: window.p)
+  std::vector<int64_t> all_rows, all_ghosts;
+  DevBuf b, r, q, r0, s, t, yout;
+  DevBuf scalars, partials, counter, halo_counter, history;
+  Scalars* hS = nullptr;  // pinned mirror
+  // launch geometry
+  int spmv_grid = 0, spmv_stages = 0, spmv_smem = 0, vec_grid = 0;
+  int evict_first = 0;
+  GraphSet cg, bicg;
+  size_t device_bytes = 0;
+  // stats of the last call
+  double last_solve_ms = 0, last_h2d_ms = 0, last_d2h_ms = 0;
+  int64_t last_launches = 0, last_iterations = 0, last_spmv = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"; \
+      return B200S_ERR_CUDA;                                                                            \
+    }                                                                                                   \
+  } while (0)
+
+int fail(b200s_handle* h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+int dev_alloc(b200s_handle* h, DevBuf& buf, size_t bytes, bool zero = false) {
+  bytes = ((bytes + 255) & ~size_t(255)) + 256;  // slack: bulk copies read up to 16 B past the logical end
+  if (buf.p && buf.bytes >= bytes) {
+    if (zero) CK(cudaMemsetAsync(buf.p, 0, buf.bytes, h->stream));
+    return 0;
+  }
+  if (buf.p) {
+    cudaFree(buf.p);
+    h->device_bytes -= buf.bytes;
+    buf.p = nullptr;
+    buf.bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&buf.p, bytes);
+  if (e != cudaSuccess) {
+    buf.p = nullptr;
+    return fail(h, B200S_ERR_ALLOC, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  }
+  buf.bytes = bytes;
+  h->device_bytes += bytes;
+  if (zero) CK(cudaMemsetAsync(buf.p, 0, bytes, h->stream));
+  return 0;
+}
+
+void dev_free(b200s_handle* h, DevBuf& buf) {
+  if (buf.p) {
+    cudaFree(buf.p);
+    h->device_bytes -= buf.bytes;
+  }
+  buf.p = nullptr;
+  buf.bytes = 0;
+}
+
+void destroy_graphs(GraphSet& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (g.graph) cudaGraphDestroy(g.graph);
+  if (g.body_exec) cudaGraphExecDestroy(g.body_exec);
+  if (g.body_graph) cudaGraphDestroy(g.body_graph);
+  g = GraphSet();
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// ---- window layout (identical arithmetic on every rank, for every rank) ----
+size_t ext_slot_bytes(int64_t rows, int64_t ghosts) {
+  return ((static_cast<size_t>(rows + ghosts) * 8 + 255) & ~size_t(255)) + 256;
+}
+enum { kSlotX = 0, kSlotP = 1, kSlotZ = 2, kSlotSpmv = 3, kNumSlots = 4 };
+
+template <typename T>
+T* slot_ptr(const b200s_handle* h, int slot) {
+  return reinterpret_cast<T*>(static_cast<char*>(h->window.p) + h->slot_bytes * slot);
+}
+
+CommDev make_comm(const b200s_handle* h) {
+  CommDev c{};
+  c.world = h->plan.world;
+  c.rank = h->plan.rank;
+  char* self = static_cast<char*>(h->window.p);
+  c.box_self = reinterpret_cast<double*>(self + h->box_off);
+  c.flag_self = reinterpret_cast<unsigned*>(self + h->flag_off);
+  c.halo_flag_self = reinterpret_cast<unsigned*>(self + h->halo_flag_off);
+  for (int q = 0; q < c.world && q < kMaxWorld; ++q) {
+    // offsets inside a peer's window depend on that peer's slot size
+    size_t sb = ext_slot_bytes(h->all_rows[q], h->all_ghosts[q]);
+    char* base = static_cast<char*>(h->peer_window[q]);
+    size_t box_off = sb * kNumSlots;
+    size_t flag_off = box_off + sizeof(double) * 2 * kMaxWorld * 4;
+    size_t halo_off = flag_off + sizeof(unsigned) * 2 * kMaxWorld;
+    c.box_peer[q] = reinterpret_cast<double*>(base + box_off);
+    c.flag_peer[q] = reinterpret_cast<unsigned*>(base + flag_off);
+    c.halo_flag_peer[q] = reinterpret_cast<unsigned*>(base + halo_off);
+  }
+  return c;
+}
+
+RedCtx make_red(const b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGraphConditionalHandle cond) {
+  RedCtx r{};
+  r.partials = h->partials.as<double>();
+  r.counter = h->counter.as<unsigned>();
+  r.S = h->scalars.as<Scalars>();
+  r.epilogue = epilogue;
+  r.gate = gate;
+  r.cond_handle = static_cast<unsigned long long>(cond);
+  r.set_cond = set_cond ? 1 : 0;
+  r.comm = make_comm(h);
+  return r;
+}
+
+unsigned recv_mask(const b200s_handle* h) {
+  unsigned m = 0;
+  for (int q = 0; q < h->plan.world; ++q)
+    if (h->plan.recv_counts[q] > 0) m |= 1u << q;
+  return m;
+}
+
+// ---- kernel launch helpers (all on h->stream; counted) ----
+template <typename T>
+int launch_spmv(b200s_handle* h, const T* x_ext, T* y, const T* w, int ndot, int epilogue, int gate, bool set_cond,
+                cudaGraphConditionalHandle cond) {
+  SpmvArgs<T> a{};
+  a.tiles = h->tiles.as<Tile>();
+  a.ntiles = static_cast<int>(h->plan.tiles.size());
+  a.first_boundary_tile = a.ntiles - h->plan.n_boundary_tiles;
+  a.rowptr = h->rowptr.as<int32_t>();
+  a.colidx = h->colidx.as<int32_t>();
+  a.vals = h->vals.as<T>();
+  a.x = x_ext;
+  a.y = y;
+  a.w = w;
+  a.stages = h->spmv_stages;
+  a.cap_nnz = h->plan.tile_nnz;
+  a.cap_rows = h->plan.tile_rows_cap;
+  a.tail_blk = (sizeof(T) == 4) ? 8 : 0;
+  a.evict_first = h->evict_first;
+  a.recv_mask = recv_mask(h);
+  a.history = h->history.as<double>();
+  a.red = make_red(h, epilogue, gate, set_cond, cond);
+  if (h->spmv_impl == B200S_SPMV_DIRECT) {
+    const int rows = static_cast<int>(h->plan.rows);
+    const int grid = h->sm_count * 8;
+#define B200S_DIRECT(LG)                                                                                   \
+  case LG:                                                                                                 \
+    if (ndot == 0) spmv_direct_kernel<T, LG, 0><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);            \
+    else if (ndot == 1) spmv_direct_kernel<T, LG, 1><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);       \
+    else spmv_direct_kernel<T, LG, 2><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);                      \
+    break;
+    switch (h->direct_lg) {
+      B200S_DIRECT(0) B200S_DIRECT(1) B200S_DIRECT(2) B200S_DIRECT(3) B200S_DIRECT(4)
+      default:
+        if (ndot == 0) spmv_direct_kernel<T, 5, 0><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);
+        else if (ndot == 1) spmv_direct_kernel<T, 5, 1><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);
+        else spmv_direct_kernel<T, 5, 2><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);
+    }
+#undef B200S_DIRECT
+  } else {
+    if (ndot == 0) spmv_staged_kernel<T, 0><<<h->spmv_grid, kSpmvThreads, h->spmv_smem, h->stream>>>(a);
+    else if (ndot == 1) spmv_staged_kernel<T, 1><<<h->spmv_grid, kSpmvThreads, h->spmv_smem, h->stream>>>(a);
+    else spmv_staged_kernel<T, 2><<<h->spmv_grid, kSpmvThreads, h->spmv_smem, h->stream>>>(a);
+  }
+  CK(cudaGetLastError());
+  h->last_launches++;
+  return 0;
+}
+
+template <typename T>
+int launch_halo(b200s_handle* h, int slot, int gate) {
+  if (h->plan.world <= 1) return 0;
+  HaloArgs<T> a{};
+  a.x = slot_ptr<T>(h, slot);
+  a.send_rows = h->send_rows.as<int32_t>();
+  for (int q = 0; q < h->plan.world; ++q) {
+    a.send_offsets[q] = h->plan.send_offsets[q];
+    a.send_counts[q] = h->plan.send_counts[q];
+    size_t sb = ext_slot_bytes(h->all_rows[q], h->all_ghosts[q]);
+    char* base = static_cast<char*>(h->peer_window[q]) + sb * slot;
+    a.dst[q] = reinterpret_cast<T*>(base) + h->all_rows[q] + h->plan.send_slot0[q];
+  }
+  a.counter = h->halo_counter.as<unsigned>();
+  a.red = make_red(h, kEpiNone, gate, false, 0);
+  int64_t n = static_cast<int64_t>(h->plan.send_rows.size());
+  int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (n + kVecThreads - 1) / kVecThreads)));
+  halo_push_kernel<T><<<grid, kVecThreads, 0, h->stream>>>(a);
+  CK(cudaGetLastError());
+  h->last_launches++;
+  return 0;
+}
+
+VecArgs make_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGraphConditionalHandle cond) {
+  VecArgs a{};
+  a.n = h->plan.rows;
+  a.x = slot_ptr<double>(h, kSlotX);
+  a.p = slot_ptr<double>(h, kSlotP);  // CG: p ; BiCGSTAB: y lives in kSlotP, p in h->yout (not exchanged)
+  a.z = slot_ptr<double>(h, kSlotZ);
+  a.r = h->r.as<double>();
+  a.q = h->q.as<double>();
+  a.r0 = h->r0.as<double>();
+  a.s = h->s.as<double>();
+  a.t = h->t.as<double>();
+  a.y = nullptr;
+  a.b = h->b.as<double>();
+  a.invdiag = h->invdiag.as<double>();
+  a.history = h->history.as<double>();
+  a.red = make_red(h, epilogue, gate, set_cond, cond);
+  return a;
+}
+
+#define LAUNCH_VEC(kernel, args)                                     \
+  do {                                                               \
+    kernel<<<h->vec_grid, kVecThreads, 0, h->stream>>>(args);        \
+    CK(cudaGetLastError());                                          \
+    h->last_launches++;                                              \
+  } while (0)
+
+// ---- the iteration bodies (enqueued either under stream capture or directly) ----
+int enqueue_cg_init(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
+  int rc;
+  if ((rc = launch_halo<double>(h, kSlotX, kGateGuess))) return rc;
+  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotX), h->q.as<double>(), nullptr, 0, kEpiNone, kGateGuess,
+                                false, 0)))
+    return rc;
+  VecArgs a = make_vec(h, kEpiCgInit, kGateNone, set_cond, cond);
+  LAUNCH_VEC(cg_init_kernel, a);
+  return 0;
+}
+
+int enqueue_cg_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
+  int rc;
+  if ((rc = launch_halo<double>(h, kSlotP, kGateLoop))) return rc;
+  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotP), h->q.as<double>(), nullptr, 1, kEpiCgPAp, kGateLoop,
+                                false, 0)))
+    return rc;
+  VecArgs u = make_vec(h, kEpiCgUpdate, kGateLoop, set_cond, cond);
+  LAUNCH_VEC(cg_update_kernel, u);
+  VecArgs d = make_vec(h, kEpiNone, kGateLoop, false, 0);
+  LAUNCH_VEC(cg_direction_kernel, d);
+  return 0;
+}
+
+// BiCGSTAB vector roles: x = slot X (ext), y = slot P (ext), z = slot Z (ext), p = h->yout, v = h->q, t = h->t
+VecArgs make_bicg_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGraphConditionalHandle cond) {
+  VecArgs a = make_vec(h, epilogue, gate, set_cond, cond);
+  a.y = slot_ptr<double>(h, kSlotP);
+  a.p = h->yout.as<double>();
+  return a;
+}
+
+int enqueue_bicg_init(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
+  int rc;
+  if ((rc = launch_halo<double>(h, kSlotX, kGateGuess))) return rc;
+  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotX), h->t.as<double>(), nullptr, 0, kEpiNone, kGateGuess,
+                                false, 0)))
+    return rc;
+  VecArgs a = make_bicg_vec(h, kEpiBiInit, kGateNone, set_cond, cond);
+  LAUNCH_VEC(bicg_init_kernel, a);
+  return 0;
+}
+
+int enqueue_bicg_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
+  int rc;
+  // re-orthogonalisation branch (BiCGSTAB.h:72-81), live only when the control state asks for it
+  if ((rc = launch_halo<double>(h, kSlotX, kGateRestart))) return rc;
+  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotX), h->t.as<double>(), nullptr, 0, kEpiNone,
+                                kGateRestart, false, 0)))
+    return rc;
+  VecArgs rs = make_bicg_vec(h, kEpiBiRestart, kGateRestart, false, 0);
+  LAUNCH_VEC(bicg_restart_kernel, rs);
+  VecArgs pa = make_bicg_vec(h, kEpiNone, kGateLoop, false, 0);
+  LAUNCH_VEC(bicg_p_kernel, pa);
+  if ((rc = launch_halo<double>(h, kSlotP, kGateLoop))) return rc;
+  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotP), h->q.as<double>(), h->r0.as<double>(), 1, kEpiBiR0V,
+                                kGateLoop, false, 0)))
+    return rc;
+  VecArgs sa = make_bicg_vec(h, kEpiNone, kGateLoop, false, 0);
+  LAUNCH_VEC(bicg_s_kernel, sa);
+  if ((rc = launch_halo<double>(h, kSlotZ, kGateLoop))) return rc;
+  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotZ), h->t.as<double>(), h->s.as<double>(), 2, kEpiBiTsTt,
+                                kGateLoop, false, 0)))
+    return rc;
+  VecArgs ua = make_bicg_vec(h, kEpiBiUpdate, kGateLoop, set_cond, cond);
+  LAUNCH_VEC(bicg_update_kernel, ua);
+  return 0;
+}
+
+int enqueue_finalize(b200s_handle* h) {
+  VecArgs a = make_vec(h, kEpiNone, kGateNone, false, 0);
+  LAUNCH_VEC(finalize_kernel, a);
+  return 0;
+}
+
+typedef int (*enqueue_fn)(b200s_handle*, bool, cudaGraphConditionalHandle);
+
+// Builds the solve graph(s) for one solver kind.
+int build_graphs(b200s_handle* h, GraphSet& g, enqueue_fn init, enqueue_fn body) {
+  if (g.built) return 0;
+  int64_t saved = h->last_launches;
+  if (h->loop_mode == B200S_LOOP_WHILE_GRAPH) {
+    CK(cudaGraphCreate(&g.graph, 0));
+    cudaGraphConditionalHandle cond;
+    CK(cudaGraphConditionalHandleCreate(&cond, g.graph, 0, cudaGraphCondAssignDefault));
+    // 1. init phase, captured straight into the top-level graph
+    CK(cudaStreamBeginCaptureToGraph(h->stream, g.graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    h->last_launches = 0;
+    int rc = init(h, true, cond);
+    g.init_kernels = static_cast<int>(h->last_launches);
+    cudaStreamCaptureStatus st;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    cudaGraph_t cap_graph = nullptr;
+    if (!rc) CK(cudaStreamGetCaptureInfo_v2(h->stream, &st, nullptr, &cap_graph, &deps, &ndeps));
+    std::vector<cudaGraphNode_t> dep_vec(deps, deps + ndeps);
+    cudaGraph_t tmp = nullptr;
+    cudaError_t ee = cudaStreamEndCapture(h->stream, &tmp);
+    if (rc) return rc;
+    CK(ee);
+    // 2. WHILE node whose body is one iteration
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    np.conditional.handle = cond;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t while_node;
+    CK(cudaGraphAddNode(&while_node, g.graph, dep_vec.data(), dep_vec.size(), &np));
+    cudaGraph_t body_graph = np.conditional.phGraph_out[0];
+    CK(cudaStreamBeginCaptureToGraph(h->stream, body_graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    h->last_launches = 0;
+    rc = body(h, true, cond);
+    g.body_kernels = static_cast<int>(h->last_launches);
+    ee = cudaStreamEndCapture(h->stream, &tmp);
+    if (rc) return rc;
+    CK(ee);
+    // 3. tail
+    CK(cudaStreamBeginCaptureToGraph(h->stream, g.graph, &while_node, nullptr, 1, cudaStreamCaptureModeRelaxed));
+    h->last_launches = 0;
+    rc = enqueue_finalize(h);
+    g.tail_kernels = static_cast<int>(h->last_launches);
+    ee = cudaStreamEndCapture(h->stream, &tmp);
+    if (rc) return rc;
+    CK(ee);
+    CK(cudaGraphInstantiate(&g.exec, g.graph, 0));
+  } else if (h->loop_mode == B200S_LOOP_CHUNKED_GRAPH) {
+    const int chunk = h->cfg.chunk_iters > 0 ? h->cfg.chunk_iters : 32;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    h->last_launches = 0;
+    int rc = init(h, false, 0);
+    g.init_kernels = static_cast<int>(h->last_launches);
+    cudaError_t ee = cudaStreamEndCapture(h->stream, &g.graph);
+    if (rc) return rc;
+    CK(ee);
+    CK(cudaGraphInstantiate(&g.exec, g.graph, 0));
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    h->last_launches = 0;
+    for (int i = 0; i < chunk && !rc; ++i) rc = body(h, false, 0);
+    g.body_kernels = static_cast<int>(h->last_launches);
+    ee = cudaStreamEndCapture(h->stream, &g.body_graph);
+    if (rc) return rc;
+    CK(ee);
+    CK(cudaGraphInstantiate(&g.body_exec, g.body_graph, 0));
+    g.tail_kernels = 1;
+  } else {
+    g.tail_kernels = 1;
+  }
+  h->last_launches = saved;
+  g.built = true;
+  return 0;
+}
+
+int ensure_solver_buffers(b200s_handle* h, bool bicg) {
+  const size_t vb = static_cast<size_t>(h->plan.rows) * 8;
+  int rc;
+  if ((rc = dev_alloc(h, h->b, vb))) return rc;
+  if ((rc = dev_alloc(h, h->r, vb))) return rc;
+  if ((rc = dev_alloc(h, h->q, vb))) return rc;
+  if (bicg) {
+    if ((rc = dev_alloc(h, h->r0, vb))) return rc;
+    if ((rc = dev_alloc(h, h->s, vb))) return rc;
+    if ((rc = dev_alloc(h, h->t, vb))) return rc;
+    if ((rc = dev_alloc(h, h->yout, vb))) return rc;
+  }
+  return 0;
+}
+
+int run_solve(b200s_handle* h, bool bicg, const double* b_dev, double* x_dev, int use_guess, double tol,
+              int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out) {
+  if (!h->factorized) return fail(h, B200S_ERR_INVALID, "solve: call analyze_pattern + factorize first (IterativeSolverBase.h:337 asserts m_isInitialized)");
+  if (h->scalar_bytes != 8) return fail(h, B200S_ERR_UNSUPPORTED, "solve: the matrix was factorized in float; solvers run in double");
+  int rc;
+  if ((rc = ensure_solver_buffers(h, bicg))) return rc;
+  GraphSet& g = bicg ? h->bicg : h->cg;
+  if ((rc = build_graphs(h, g, bicg ? enqueue_bicg_init : enqueue_cg_init, bicg ? enqueue_bicg_body : enqueue_cg_body)))
+    return rc;
+
+  const int64_t n = h->plan.rows;
+  if (tol < 0) tol = std::numeric_limits<double>::epsilon();  // IterativeSolverBase.h:413
+  if (max_iters < 0) max_iters = 2 * h->plan.cols;             // :281-284
+  double* x_int = slot_ptr<double>(h, kSlotX);
+  if (b_dev != h->b.as<double>()) CK(cudaMemcpyAsync(h->b.p, b_dev, n * 8, cudaMemcpyDeviceToDevice, h->stream));
+  if (use_guess && x_dev != x_int) CK(cudaMemcpyAsync(x_int, x_dev, n * 8, cudaMemcpyDeviceToDevice, h->stream));
+  // solve inputs -> device control block (first 24 bytes of Scalars)
+  h->hS->tol = tol;
+  h->hS->max_iters = max_iters;
+  h->hS->use_guess = use_guess ? 1 : 0;
+  h->hS->pad0 = 0;
+  CK(cudaMemcpyAsync(h->scalars.p, h->hS, 24, cudaMemcpyHostToDevice, h->stream));
+
+  h->last_launches = 0;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  if (h->loop_mode == B200S_LOOP_WHILE_GRAPH) {
+    CK(cudaGraphLaunch(g.exec, h->stream));
+  } else {
+    if (h->loop_mode == B200S_LOOP_CHUNKED_GRAPH) {
+      CK(cudaGraphLaunch(g.exec, h->stream));
+      h->last_launches += g.init_kernels;
+    } else {
+      if ((rc = (bicg ? enqueue_bicg_init : enqueue_cg_init)(h, false, 0))) return rc;
+    }
+    for (;;) {
+      CK(cudaMemcpyAsync(h->hS, h->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (h->hS->stop) break;
+      if (h->loop_mode == B200S_LOOP_CHUNKED_GRAPH) {
+        CK(cudaGraphLaunch(g.body_exec, h->stream));
+        h->last_launches += g.body_kernels;
+      } else {
+        if ((rc = (bicg ? enqueue_bicg_body : enqueue_cg_body)(h, false, 0))) return rc;
+      }
+    }
+    if ((rc = enqueue_finalize(h))) return rc;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaMemcpyAsync(h->hS, h->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+  if (x_dev != x_int) CK(cudaMemcpyAsync(x_dev, x_int, n * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_solve_ms = ms;
+
+  const Scalars& S = *h->hS;
+  int64_t iters;
+  double err;
+  if (bicg && S.rhs_zero) {  // BiCGSTAB.h:47-51 returns before touching iters / tol_error
+    iters = max_iters;
+    err = tol;
+  } else if (S.rhs_zero) {   // ConjugateGradient.h:46-52
+    iters = 0;
+    err = 0.0;
+  } else {
+    iters = S.iter;
+    err = std::sqrt(S.rr / S.bb);  // ConjugateGradient.h:89 / BiCGSTAB.h:104
+  }
+  int info = (err <= tol) ? 0 : 2;  // ConjugateGradient.h:220 / BiCGSTAB.h:201-203
+  if (S.numerical_issue) info = 1;
+  if (iters_out) *iters_out = iters;
+  if (error_out) *error_out = err;
+  if (info_out) *info_out = info;
+  h->last_iterations = iters;
+  h->last_spmv = S.spmv_count;
+  if (h->loop_mode == B200S_LOOP_WHILE_GRAPH) {
+    // body executions: one per SpMV launched inside the loop (CG: 1 per pass; BiCGSTAB: 2 per pass + restarts)
+    int64_t init_spmv = use_guess ? 1 : 0;
+    if (bicg) init_spmv = 1;  // counted by kEpiBiInit regardless (the gated launch still happens)
+    int64_t loop_spmv = std::max<int64_t>(0, S.spmv_count - init_spmv);
+    int64_t passes = bicg ? (loop_spmv - S.restarts + 1) / 2 : loop_spmv;
+    h->last_launches = g.init_kernels + passes * g.body_kernels + g.tail_kernels;
+  }
+  return 0;
+}
+
+template <typename T>
+int factorize_impl(b200s_handle* h, const T* values, int precond) {
+  if (!h->analyzed) return fail(h, B200S_ERR_INVALID, "factorize: call analyze_pattern first (IterativeSolverBase.h:218 asserts m_analysisIsOk)");
+  if (!values && h->plan.input_nnz > 0) return fail(h, B200S_ERR_INVALID, "factorize: values is null");
+  if (precond != B200S_PRECOND_IDENTITY && precond != B200S_PRECOND_JACOBI)
+    return fail(h, B200S_ERR_INVALID, "factorize: precond must be 0 (identity) or 1 (Jacobi)");
+  CK(cudaSetDevice(h->device));
+  const Plan& p = h->plan;
+  int rc;
+  if ((rc = dev_alloc(h, h->vals, static_cast<size_t>(p.nnz) * sizeof(T) + 64))) return rc;
+  if (h->scalar_bytes != static_cast<int>(sizeof(T))) {  // graphs bake pointers/types: rebuild lazily
+    destroy_graphs(h->cg);
+    destroy_graphs(h->bicg);
+  }
+  h->scalar_bytes = sizeof(T);
+  h->precond = precond;
+  cudaEvent_t e0 = h->ev0, e1 = h->ev1;
+  CK(cudaEventRecord(e0, h->stream));
+  if (p.src.empty()) {
+    if (p.nnz) CK(cudaMemcpyAsync(h->vals.p, values, static_cast<size_t>(p.nnz) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    DevBuf staging;
+    if ((rc = dev_alloc(h, staging, static_cast<size_t>(p.input_nnz) * sizeof(T) + 64))) return rc;
+    if (p.input_nnz) CK(cudaMemcpyAsync(staging.p, values, static_cast<size_t>(p.input_nnz) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    if (p.nnz) {
+      gather_values_kernel<T><<<h->sm_count * 4, 256, 0, h->stream>>>(p.nnz, h->src.as<int32_t>(), staging.as<T>(), h->vals.as<T>());
+      CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    dev_free(h, staging);
+  }
+  if ((rc = dev_alloc(h, h->invdiag, static_cast<size_t>(p.rows) * sizeof(T)))) return rc;
+  if (p.rows) {
+    // the diagonal of local row j sits at local column j (owned columns are numbered like the rows)
+    jacobi_factorize_kernel<T><<<static_cast<int>((p.rows + 255) / 256), 256, 0, h->stream>>>(
+        static_cast<int>(p.rows), h->rowptr.as<int32_t>(), h->colidx.as<int32_t>(), h->vals.as<T>(), h->invdiag.as<T>(),
+        precond == B200S_PRECOND_IDENTITY);
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  h->last_h2d_ms = ms;
+  h->factorized = true;
+  return 0;
+}
+
+template <typename T>
+int spmv_device_impl(b200s_handle* h, const T* x_dev, T* y_dev, int reps, float* ms_avg) {
+  if (!h->factorized) return fail(h, B200S_ERR_INVALID, "spmv: call analyze_pattern + factorize first");
+  if (h->scalar_bytes != static_cast<int>(sizeof(T))) return fail(h, B200S_ERR_INVALID, "spmv: scalar type differs from factorize");
+  if (!x_dev || !y_dev) return fail(h, B200S_ERR_INVALID, "spmv: null pointer");
+  CK(cudaSetDevice(h->device));
+  if (reps < 1) reps = 1;
+  const T* x_ext = x_dev;
+  h->last_launches = 0;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < reps; ++i) {
+    int rc;
+    if (h->plan.world > 1) {
+      T* xs = slot_ptr<T>(h, kSlotSpmv);
+      if (x_dev != xs) CK(cudaMemcpyAsync(xs, x_dev, static_cast<size_t>(h->plan.rows) * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+      if ((rc = launch_halo<T>(h, kSlotSpmv, kGateNone))) return rc;
+      x_ext = xs;
+      // a cross-rank rendezvous after each product keeps single-buffered ghost slots safe for the next push
+      if ((rc = launch_spmv<T>(h, x_ext, y_dev, nullptr, 0, kEpiSpmvOnly, kGateNone, false, 0))) return rc;
+    } else {
+      if ((rc = launch_spmv<T>(h, x_ext, y_dev, nullptr, 0, kEpiNone, kGateNone, false, 0))) return rc;
+    }
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (ms_avg) *ms_avg = ms / reps;
+  h->last_solve_ms = ms;
+  return 0;
+}
+
+template <typename T>
+int spmv_host_impl(b200s_handle* h, const T* x, T* y) {
+  if (!h->factorized) return fail(h, B200S_ERR_INVALID, "spmv: call analyze_pattern + factorize first");
+  if (!x || !y) return fail(h, B200S_ERR_INVALID, "spmv: null pointer");
+  CK(cudaSetDevice(h->device));
+  const Plan& p = h->plan;
+  const int64_t nx = (p.world == 1) ? p.cols : p.rows;
+  T* xs = slot_ptr<T>(h, kSlotSpmv);
+  int rc;
+  if ((rc = dev_alloc(h, h->yout, static_cast<size_t>(p.rows) * 8))) return rc;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaMemcpyAsync(xs, x, static_cast<size_t>(nx) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_h2d_ms = ms;
+  float k_ms = 0;
+  if ((rc = spmv_device_impl<T>(h, xs, h->yout.as<T>(), 1, &k_ms))) return rc;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaMemcpyAsync(y, h->yout.p, static_cast<size_t>(p.rows) * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_d2h_ms = ms;
+  h->last_solve_ms = k_ms;
+  return 0;
+}
+
+int solve_host(b200s_handle* h, bool bicg, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
+               int64_t* iters_out, double* error_out, int* info_out) {
+  if (!h) return B200S_ERR_INVALID;
+  if (!h->factorized) return fail(h, B200S_ERR_INVALID, "solve: call analyze_pattern + factorize first");
+  if (!b || !x) return fail(h, B200S_ERR_INVALID, "solve: null pointer");
+  CK(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = ensure_solver_buffers(h, bicg))) return rc;
+  const size_t vb = static_cast<size_t>(h->plan.rows) * 8;
+  cudaEvent_t e0 = h->ev0, e1 = h->ev1;
+  CK(cudaEventRecord(e0, h->stream));
+  CK(cudaMemcpyAsync(h->b.p, b, vb, cudaMemcpyHostToDevice, h->stream));
+  if (use_guess) CK(cudaMemcpyAsync(slot_ptr<double>(h, kSlotX), x, vb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  h->last_h2d_ms = ms;
+  if ((rc = run_solve(h, bicg, h->b.as<double>(), slot_ptr<double>(h, kSlotX), use_guess, tol, max_iters, iters_out,
+                      error_out, info_out)))
+    return rc;
+  double solve_ms = h->last_solve_ms;
+  CK(cudaEventRecord(e0, h->stream));
+  CK(cudaMemcpyAsync(x, slot_ptr<double>(h, kSlotX), vb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  h->last_d2h_ms = ms;
+  h->last_solve_ms = solve_ms;
+  return 0;
+}
+
+int configure_spmv(b200s_handle* h) {
+  // stage geometry is decided for the widest scalar (double) so that one plan serves both precisions
+  const Plan& p = h->plan;
+  size_t stage = spmv_stage_bytes<double>(p.tile_nnz, p.tile_rows_cap);
+  int stages = env_int("B200S_SPMV_STAGES", 4);
+  stages = std::max(2, std::min(8, stages));
+  size_t budget = 110 * 1024;  // two CTAs per SM out of 227 KB
+  while (stages > 2 && stage * stages > budget) --stages;
+  if (stage * stages > 220 * 1024) return fail(h, B200S_ERR_INVALID, "tile_nnz/tile_rows too large for shared memory");
+  h->spmv_stages = stages;
+  h->spmv_smem = static_cast<int>(stage * stages);
+  const void* fns[] = {
+      (const void*)spmv_staged_kernel<double, 0>, (const void*)spmv_staged_kernel<double, 1>,
+      (const void*)spmv_staged_kernel<double, 2>, (const void*)spmv_staged_kernel<float, 0>,
+      (const void*)spmv_staged_kernel<float, 1>,  (const void*)spmv_staged_kernel<float, 2>};
+  for (const void* f : fns) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, h->spmv_smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_staged_kernel<double, 1>, kSpmvThreads, h->spmv_smem));
+  if (occ < 1) return fail(h, B200S_ERR_CUDA, "staged SpMV kernel does not fit on an SM");
+  occ = std::min(occ, env_int("B200S_SPMV_OCC", 2));
+  int grid = h->sm_count * occ;
+  int ntiles = static_cast<int>(p.tiles.size());
+  grid = std::max(1, std::min(grid, std::max(1, ntiles)));
+  h->spmv_grid = std::min(grid, kMaxGrid);
+  int64_t n2 = std::max<int64_t>(1, p.rows / 2);
+  int64_t vg = std::min<int64_t>(static_cast<int64_t>(h->sm_count) * env_int("B200S_VEC_CTAS_PER_SM", 6),
+                                 (n2 + kVecThreads - 1) / kVecThreads);
+  h->vec_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(vg, kMaxGrid)));
+  // direct kernel: lanes per row from the global mean row length
+  int mean = p.rows ? static_cast<int>((p.nnz + p.rows - 1) / p.rows) : 1;
+  int lg = 0;
+  while ((1 << lg) < std::max(1, mean / 2) && lg < 5) ++lg;
+  h->direct_lg = lg;
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int b200s_version(void) { return B200S_VERSION; }
+
+int b200s_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+const char* b200s_last_error(const b200s_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int b200s_create(const b200s_config* cfg, b200s_handle** out) {
+  if (!out) return B200S_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device: this library has no CPU path (sm_100a kernels only)";
+    return B200S_ERR_NO_DEVICE;
+  }
+  b200s_handle* h = new b200s_handle();
+  h->cfg.struct_size = sizeof(b200s_config);
+  h->cfg.device = -1;
+  h->cfg.world = 1;
+  if (cfg) std::memcpy(&h->cfg, cfg, std::min<size_t>(sizeof(b200s_config), cfg->struct_size > 0 ? cfg->struct_size : sizeof(b200s_config)));
+  if (h->cfg.world <= 0) h->cfg.world = 1;
+  auto bail = [&](int code, const std::string& m) {
+    g_create_error = m;
+    delete h;
+    return code;
+  };
+  if (h->cfg.world > kMaxWorld) return bail(B200S_ERR_UNSUPPORTED, "world > 8 (one NVSwitch box)");
+  int dev = h->cfg.device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return bail(B200S_ERR_CUDA, "cudaGetDevice failed");
+  if (dev >= ndev) return bail(B200S_ERR_INVALID, "device ordinal out of range");
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10)
+    return bail(B200S_ERR_NO_DEVICE, "device " + std::to_string(dev) + " is sm_" + std::to_string(major) + std::to_string(minor) +
+                                         "; this library ships sm_100a code only and has no fallback");
+  h->device = dev;
+  if (cudaSetDevice(dev) != cudaSuccess) return bail(B200S_ERR_CUDA, "cudaSetDevice failed");
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&h->hS), sizeof(Scalars)) != cudaSuccess) {
+    std::string m = std::string("stream/event creation failed: ") + cudaGetErrorString(cudaGetLastError());
+    b200s_destroy(h);
+    g_create_error = m;
+    return B200S_ERR_CUDA;
+  }
+  std::memset(h->hS, 0, sizeof(Scalars));
+  h->loop_mode = h->cfg.loop_mode ? h->cfg.loop_mode : env_int("B200S_LOOP_MODE", B200S_LOOP_WHILE_GRAPH);
+  h->spmv_impl = h->cfg.spmv_impl ? h->cfg.spmv_impl : env_int("B200S_SPMV_IMPL", B200S_SPMV_STAGED);
+  h->evict_first = env_int("B200S_EVICT_FIRST", 0);
+  if (h->cfg.tile_nnz <= 0) h->cfg.tile_nnz = env_int("B200S_TILE_NNZ", 0);
+  if (h->cfg.tile_rows <= 0) h->cfg.tile_rows = env_int("B200S_TILE_ROWS", 0);
+  *out = h;
+  return B200S_OK;
+}
+
+void b200s_destroy(b200s_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  destroy_graphs(h->cg);
+  destroy_graphs(h->bicg);
+  for (int q = 0; q < static_cast<int>(h->peer_window.size()); ++q)
+    if (q != h->plan.rank && h->peer_window[q]) cudaIpcCloseMemHandle(h->peer_window[q]);
+  DevBuf* bufs[] = {&h->rowptr, &h->colidx, &h->vals, &h->src, &h->tiles, &h->invdiag, &h->send_rows, &h->window,
+                    &h->b, &h->r, &h->q, &h->r0, &h->s, &h->t, &h->yout, &h->scalars, &h->partials, &h->counter,
+                    &h->halo_counter, &h->history};
+  for (DevBuf* b : bufs) dev_free(h, *b);
+  if (h->hS) cudaFreeHost(h->hS);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t nnz, const int32_t* rowptr,
+                          const int32_t* colidx, const int32_t* inner_nnz, int uplo, const int64_t* row_starts) {
+  if (!h) return B200S_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  h->analyzed = h->factorized = false;
+  destroy_graphs(h->cg);
+  destroy_graphs(h->bicg);
+  std::string err;
+  int rc = build_plan(h->cfg, rows, cols, nnz, rowptr, colidx, inner_nnz, uplo, row_starts, h->plan, err);
+  if (rc) return fail(h, rc, err);
+  const Plan& p = h->plan;
+  if ((rc = configure_spmv(h))) return rc;
+
+  // ---- pattern -> device ----
+  if ((rc = dev_alloc(h, h->rowptr, static_cast<size_t>(p.rows + 1) * 4 + 64))) return rc;
+  if ((rc = dev_alloc(h, h->colidx, static_cast<size_t>(p.nnz) * 4 + 64))) return rc;
+  if ((rc = dev_alloc(h, h->tiles, std::max<size_t>(1, p.tiles.size()) * sizeof(Tile)))) return rc;
+  CK(cudaMemcpyAsync(h->rowptr.p, p.rowptr.data(), static_cast<size_t>(p.rows + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (p.nnz) CK(cudaMemcpyAsync(h->colidx.p, p.colidx_ptr(), static_cast<size_t>(p.nnz) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (!p.tiles.empty()) CK(cudaMemcpyAsync(h->tiles.p, p.tiles.data(), p.tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, h->stream));
+  if (!p.src.empty()) {
+    if ((rc = dev_alloc(h, h->src, p.src.size() * 4))) return rc;
+    CK(cudaMemcpyAsync(h->src.p, p.src.data(), p.src.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (!p.send_rows.empty()) {
+    if ((rc = dev_alloc(h, h->send_rows, p.send_rows.size() * 4))) return rc;
+    CK(cudaMemcpyAsync(h->send_rows.p, p.send_rows.data(), p.send_rows.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  if ((rc = dev_alloc(h, h->scalars, sizeof(Scalars), true))) return rc;
+  if ((rc = dev_alloc(h, h->partials, sizeof(double) * kMaxGrid * 4, true))) return rc;
+  if ((rc = dev_alloc(h, h->counter, 64, true))) return rc;
+  if ((rc = dev_alloc(h, h->halo_counter, 64, true))) return rc;
+  if ((rc = dev_alloc(h, h->history, sizeof(double) * kHistoryCap, true))) return rc;
+
+  // ---- peer-visible window: 4 extended vector slots + all-reduce mailboxes + halo flags ----
+  const int W = p.world;
+  h->all_rows.assign(W, 0);
+  h->all_ghosts.assign(W, 0);
+  int64_t mine[2] = {p.rows, static_cast<int64_t>(p.ghost_cols.size())};
+  if (W > 1) {
+    std::vector<int64_t> all(2 * W);
+    if (h->cfg.allgather(h->cfg.allgather_ctx, mine, all.data(), sizeof(mine))) return fail(h, B200S_ERR_COMM, "allgather(rows, ghosts) failed");
+    for (int q = 0; q < W; ++q) { h->all_rows[q] = all[2 * q]; h->all_ghosts[q] = all[2 * q + 1]; }
+  } else {
+    h->all_rows[0] = mine[0];
+    h->all_ghosts[0] = mine[1];
+  }
+  h->slot_bytes = ext_slot_bytes(p.rows, mine[1]);
+  h->box_off = h->slot_bytes * kNumSlots;
+  h->flag_off = h->box_off + sizeof(double) * 2 * kMaxWorld * 4;
+  h->halo_flag_off = h->flag_off + sizeof(unsigned) * 2 * kMaxWorld;
+  h->window_bytes = h->halo_flag_off + sizeof(unsigned) * kMaxWorld + 256;
+  for (int q = 0; q < static_cast<int>(h->peer_window.size()); ++q)
+    if (q != p.rank && h->peer_window[q]) cudaIpcCloseMemHandle(h->peer_window[q]);
+  h->peer_window.assign(W, nullptr);
+  if (h->window.p) { dev_free(h, h->window); }
+  if ((rc = dev_alloc(h, h->window, h->window_bytes, true))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->peer_window[p.rank] = h->window.p;
+  if (W > 1) {
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->window.p));
+    std::vector<cudaIpcMemHandle_t> all(W);
+    if (h->cfg.allgather(h->cfg.allgather_ctx, &mh, all.data(), sizeof(mh))) return fail(h, B200S_ERR_COMM, "allgather(ipc handles) failed");
+    for (int q = 0; q < W; ++q)
+      if (q != p.rank) CK(cudaIpcOpenMemHandle(&h->peer_window[q], all[q], cudaIpcMemLazyEnablePeerAccess));
+    // nobody may start pushing before everyone has mapped everyone
+    int64_t token = 1;
+    std::vector<int64_t> tokens(W);
+    if (h->cfg.allgather(h->cfg.allgather_ctx, &token, tokens.data(), sizeof(token))) return fail(h, B200S_ERR_COMM, "allgather(barrier) failed");
+  }
+  h->analyzed = true;
+  return B200S_OK;
+}
+
+int b200s_factorize_f64(b200s_handle* h, const double* values, int precond) {
+  if (!h) return B200S_ERR_INVALID;
+  return factorize_impl<double>(h, values, precond);
+}
+int b200s_factorize_f32(b200s_handle* h, const float* values, int precond) {
+  if (!h) return B200S_ERR_INVALID;
+  return factorize_impl<float>(h, values, precond);
+}
+
+int b200s_spmv_f64(b200s_handle* h, const double* x, double* y) { return h ? spmv_host_impl<double>(h, x, y) : B200S_ERR_INVALID; }
+int b200s_spmv_f32(b200s_handle* h, const float* x, float* y) { return h ? spmv_host_impl<float>(h, x, y) : B200S_ERR_INVALID; }
+int b200s_spmv_device_f64(b200s_handle* h, const double* x, double* y, int reps, float* ms) {
+  return h ? spmv_device_impl<double>(h, x, y, reps, ms) : B200S_ERR_INVALID;
+}
+int b200s_spmv_device_f32(b200s_handle* h, const float* x, float* y, int reps, float* ms) {
+  return h ? spmv_device_impl<float>(h, x, y, reps, ms) : B200S_ERR_INVALID;
+}
+
+int b200s_cg_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
+                       int64_t* iters_out, double* error_out, int* info_out) {
+  return solve_host(h, false, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
+}
+int b200s_bicgstab_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol,
+                             int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out) {
+  return solve_host(h, true, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
+}
+int b200s_cg_solve_device_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol,
+                              int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out) {
+  if (!h) return B200S_ERR_INVALID;
+  if (!b || !x) return fail(h, B200S_ERR_INVALID, "solve: null pointer");
+  CK(cudaSetDevice(h->device));
+  return run_solve(h, false, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
+}
+int b200s_bicgstab_solve_device_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol,
+                                    int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out) {
+  if (!h) return B200S_ERR_INVALID;
+  if (!b || !x) return fail(h, B200S_ERR_INVALID, "solve: null pointer");
+  CK(cudaSetDevice(h->device));
+  return run_solve(h, true, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
+}
+
+int b200s_get_stats(b200s_handle* h, b200s_stats* out) {
+  if (!h || !out) return B200S_ERR_INVALID;
+  b200s_stats st;
+  std::memset(&st, 0, sizeof(st));
+  fill_tile_stats(h->plan, &st);
+  st.device = h->device;
+  st.spmv_grid = h->spmv_grid;
+  st.spmv_block = kSpmvThreads;
+  st.spmv_smem_bytes = h->spmv_smem;
+  st.spmv_stages = h->spmv_stages;
+  st.vec_grid = h->vec_grid;
+  st.vec_block = kVecThreads;
+  st.loop_mode = h->loop_mode;
+  st.sm_count = h->sm_count;
+  st.last_solve_ms = h->last_solve_ms;
+  st.last_h2d_ms = h->last_h2d_ms;
+  st.last_d2h_ms = h->last_d2h_ms;
+  st.last_kernel_launches = h->last_launches;
+  st.last_iterations = h->last_iterations;
+  st.last_spmv_count = h->last_spmv;
+  st.device_bytes = static_cast<int64_t>(h->device_bytes);
+  int32_t want = out->struct_size > 0 ? out->struct_size : static_cast<int32_t>(sizeof(b200s_stats));
+  st.struct_size = std::min<int32_t>(want, sizeof(b200s_stats));
+  std::memcpy(out, &st, st.struct_size);
+  return B200S_OK;
+}
+
+int b200s_get_invdiag_f64(b200s_handle* h, double* invdiag) {
+  if (!h || !invdiag) return B200S_ERR_INVALID;
+  if (!h->factorized || h->scalar_bytes != 8) return fail(h, B200S_ERR_INVALID, "get_invdiag: factorize_f64 first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(invdiag, h->invdiag.p, static_cast<size_t>(h->plan.rows) * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B200S_OK;
+}
+
+int64_t b200s_get_residual_history(b200s_handle* h, double* rr, int64_t cap) {
+  if (!h || !rr || cap < 0) return B200S_ERR_INVALID;
+  if (!h->hS) return 0;
+  int64_t n = std::min<int64_t>(cap, std::min<int64_t>(h->hS->hist_len, kHistoryCap));
+  if (n > 0) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(rr, h->history.p, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return n;
+}
+
+int64_t b200s_plan_probe(const b200s_config* cfg, int64_t rows, int64_t cols, int64_t nnz, const int32_t* rowptr,
+                         const int32_t* colidx, const int64_t* row_starts, int32_t* local_colidx,
+                         int64_t* ghost_cols, int64_t ghost_cap, int32_t* send_rows, int64_t send_cap,
+                         int64_t* send_counts, int64_t* recv_counts, b200s_stats* tile_stats) {
+  b200s_config c;
+  std::memset(&c, 0, sizeof(c));
+  c.world = 1;
+  if (cfg) std::memcpy(&c, cfg, std::min<size_t>(sizeof(c), cfg->struct_size > 0 ? cfg->struct_size : sizeof(c)));
+  if (c.world <= 0) c.world = 1;
+  Plan p;
+  std::string err;
+  int rc = build_plan(c, rows, cols, nnz, rowptr, colidx, nullptr, B200S_BOTH, row_starts, p, err);
+  if (rc) {
+    g_create_error = err;
+    return rc;
+  }
+  if (local_colidx && p.nnz) std::memcpy(local_colidx, p.colidx_ptr(), static_cast<size_t>(p.nnz) * 4);
+  if (ghost_cols)
+    for (int64_t g = 0; g < std::min<int64_t>(ghost_cap, p.ghost_cols.size()); ++g) ghost_cols[g] = p.ghost_cols[g];
+  if (send_rows)
+    for (int64_t k = 0; k < std::min<int64_t>(send_cap, p.send_rows.size()); ++k) send_rows[k] = p.send_rows[k];
+  for (int q = 0; q < p.world; ++q) {
+    if (send_counts) send_counts[q] = p.send_counts[q];
+    if (recv_counts) recv_counts[q] = p.recv_counts[q];
+  }
+  if (tile_stats) {
+    int32_t want = tile_stats->struct_size > 0 ? tile_stats->struct_size : static_cast<int32_t>(sizeof(b200s_stats));
+    b200s_stats st;
+    std::memset(&st, 0, sizeof(st));
+    fill_tile_stats(p, &st);
+    st.struct_size = std::min<int32_t>(want, sizeof(b200s_stats));
+    std::memcpy(tile_stats, &st, st.struct_size);
+  }
+  return static_cast<int64_t>(p.ghost_cols.size());
+}
+
+}  // extern "C"

@@ -1,0 +1,851 @@
+// kernels.cuh -- hand-written sm_100a kernels of the sparse iterative-solve path.
+//
+//   spmv_staged_kernel   persistent CSR SpMV: matrix tiles streamed into shared memory by the bulk async-copy
+//                        engine (cp.async.bulk + mbarrier, SASS UBLKCP), rows reduced from shared memory with a
+//                        per-tile lanes-per-row choice, x gathered through L1/L2, optional fused dot products.
+//   spmv_direct_kernel   plain sub-warp-per-row CSR SpMV from global memory (A/B baseline for the ncu evidence).
+//   cg_* / bicg_*        the vector updates of ConjugateGradient.h:63-87 and BiCGSTAB.h:82-102, each fused with
+//                        the dot products that follow it.
+//   halo_push_kernel     boundary entries of a vector stored into the neighbours' ghost slots over NVLink.
+//
+// Reductions are deterministic: every thread accumulates a fixed set of elements in a fixed order, warps are
+// folded with shuffles, warps of a CTA in a fixed tree, CTAs by the last-arriving CTA in index order, ranks in
+// rank order.  No floating-point atomics anywhere.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+
+#include "device_state.h"
+
+namespace b200s {
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, no tensor map needed).
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------------- rounding-explicit arithmetic
+// The reference's SpMV row loop rounds each product and each add separately (see oracle/oracle_body.h); the other
+// updates are contracted to FMAs.  Both are spelled out so that nvcc's own contraction cannot change them.
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// ------------------------------------------------------------------------------------------- block reductions
+template <int NV>
+__device__ __forceinline__ void warp_reduce(double (&v)[NV]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+}
+
+// All threads call; result valid in thread 0.  THREADS is a multiple of 32, <= 1024.
+template <int NV, int THREADS>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double* scratch /* [32*NV] shared */) {
+  warp_reduce<NV>(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // scratch may still be in use by a previous call
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) scratch[warp * NV + j] = v[j];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = (lane < THREADS / 32) ? scratch[lane * NV + j] : 0.0;
+    warp_reduce<NV>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------- cross-rank all-reduce (one thread)
+// One-shot all-gather of the per-rank partials into every peer's mailbox over NVLink peer stores, then a sum in
+// rank order, so every rank obtains bit-identical scalars and takes identical branches.  Two mailbox parities: a
+// rank can be at most one reduction ahead of the slowest reader (it needs that reader's next partial to advance).
+__device__ __forceinline__ void allreduce_ranks(const CommDev& c, Scalars* S, double* v, int n) {
+  const unsigned seq = ++S->red_seq;
+  if (c.world <= 1) return;
+  const int par = seq & 1;
+  for (int q = 0; q < c.world; ++q) {
+    double* box = ((q == c.rank) ? c.box_self : c.box_peer[q]) + (par * kMaxWorld + c.rank) * 4;
+    for (int j = 0; j < n; ++j) st_relaxed_sys_f64(box + j, v[j]);
+  }
+  __threadfence_system();
+  for (int q = 0; q < c.world; ++q) {
+    unsigned* flag = ((q == c.rank) ? c.flag_self : c.flag_peer[q]) + par * kMaxWorld + c.rank;
+    st_release_sys(flag, seq);
+  }
+  for (int j = 0; j < n; ++j) v[j] = 0.0;
+  for (int src = 0; src < c.world; ++src) {
+    const unsigned* flag = c.flag_self + par * kMaxWorld + src;
+    while (ld_acquire_sys(flag) != seq) {
+    }
+    const double* box = c.box_self + (par * kMaxWorld + src) * 4;
+    for (int j = 0; j < n; ++j) v[j] += ld_relaxed_sys_f64(box + j);
+  }
+}
+
+// --------------------------------------------------------------------------------- scalar logic of the solvers
+// Runs in exactly one thread per reduction, after the values are reduced over CTAs and ranks.  This is the
+// reference's host-side control flow moved onto the device (citations per case).
+__device__ inline void run_epilogue(const RedCtx& ctx, const double* v, double* history) {
+  Scalars* S = ctx.S;
+  switch (ctx.epilogue) {
+    case kEpiCgInit: {  // ConjugateGradient.h:45-67
+      const double bb = v[0], rr = v[1], rz = v[2];
+      S->bb = bb; S->rr = rr; S->iter = 0; S->converged = 0; S->rhs_zero = 0; S->stop = 0; S->numerical_issue = 0;
+      S->hist_len = 0; S->spmv_count = S->use_guess ? 1 : 0;
+      if (bb == 0.0) { S->rhs_zero = 1; S->stop = 1; S->rr = 0.0; break; }   // :46-52 (error = 0)
+      double thr = S->tol * S->tol * bb;                                      // :53-54
+      if (thr < DBL_MIN) thr = DBL_MIN;
+      S->thr = thr;
+      if (rr < thr) { S->stop = 1; S->converged = 1; break; }                 // :56-61
+      S->abs_new = rz;                                                        // :67
+      if (!(rr == rr) || !(bb == bb)) { S->numerical_issue = 1; S->stop = 1; }
+      if (S->max_iters <= 0) S->stop = 1;                                     // while(i < maxIters) never entered
+    } break;
+    case kEpiCgPAp: {  // :73
+      S->pAp = v[0];
+      S->alpha = S->abs_new / v[0];
+      S->spmv_count++;
+    } break;
+    case kEpiCgUpdate: {  // :77-87
+      const double rr = v[0], rz = v[1];
+      S->rr = rr;
+      if (history && S->hist_len < kHistoryCap) history[S->hist_len++] = rr;
+      if (rr < S->thr) { S->stop = 1; S->converged = 1; break; }  // :78-79 break before i++
+      if (!(rr == rr)) { S->numerical_issue = 1; S->stop = 1; break; }
+      S->abs_old = S->abs_new;
+      S->abs_new = rz;                  // :84
+      S->beta = rz / S->abs_old;        // :85
+      S->iter++;                        // :87
+      if (S->iter >= S->max_iters) S->stop = 1;
+    } break;
+    case kEpiBiInit: {  // BiCGSTAB.h:45-65
+      const double bb = v[0], rr = v[1];
+      S->bb = bb; S->rr = rr; S->r0_sqnorm = rr; S->iter = 0; S->restarts = 0; S->converged = 0; S->rhs_zero = 0;
+      S->stop = 0; S->numerical_issue = 0; S->restart = 0; S->hist_len = 0; S->spmv_count = 1;
+      if (bb == 0.0) { S->rhs_zero = 1; S->stop = 1; break; }  // :47-51 (iters / tol_error untouched)
+      S->rho_old = 1.0; S->alpha = 1.0; S->w = 1.0;            // :52-54
+      S->thr = S->tol * S->tol * bb;                           // :62
+      S->eps2 = DBL_EPSILON * DBL_EPSILON;                     // :63
+      if (!(rr > S->thr && 0 < S->max_iters)) { S->stop = 1; S->converged = !(rr > S->thr); break; }  // :67
+      S->rho = rr;                                             // :71 r0.dot(r) with r0 == r
+      S->restart = (fabs(S->rho) < S->eps2 * S->r0_sqnorm) ? 1 : 0;  // :72
+    } break;
+    case kEpiBiR0V: {  // :89
+      S->r0v = v[0];
+      S->alpha = S->rho / v[0];
+      S->spmv_count++;
+    } break;
+    case kEpiBiTsTt: {  // :95-99
+      S->ts = v[0]; S->tt = v[1];
+      S->w = (v[1] > 0.0) ? v[0] / v[1] : 0.0;
+      S->spmv_count++;
+    } break;
+    case kEpiBiUpdate: {  // :100-102 then the loop head :67-72 of the next iteration
+      const double rr = v[0], rho_next = v[1];
+      S->rr = rr;
+      S->iter++;
+      if (history && S->hist_len < kHistoryCap) history[S->hist_len++] = rr;
+      if (!(rr > S->thr && S->iter < S->max_iters)) { S->stop = 1; S->converged = !(rr > S->thr); break; }
+      S->rho_old = S->rho;
+      S->rho = rho_next;
+      S->restart = (fabs(S->rho) < S->eps2 * S->r0_sqnorm) ? 1 : 0;
+    } break;
+    case kEpiBiRestart: {  // :76-80
+      S->rho = S->r0_sqnorm = v[0];
+      if (S->restarts++ == 0) S->iter = 0;
+      S->restart = 0;
+      S->spmv_count++;
+    } break;
+    default: break;
+  }
+}
+
+__device__ __forceinline__ bool gated_out(const Scalars* S, int gate) {
+  switch (gate) {
+    case kGateLoop: return S->stop != 0;
+    case kGateRestart: return S->stop != 0 || S->restart == 0;
+    case kGateGuess: return S->use_guess == 0;
+    default: return false;
+  }
+}
+
+// Final stage of every reduction: publish this CTA's partials, take a ticket; the last CTA folds all partials in
+// CTA order, all-reduces over ranks, runs the scalar epilogue and (in WHILE-graph mode) sets the loop condition.
+template <int NV, int THREADS>
+__device__ __forceinline__ void finish_reduction(const RedCtx& ctx, double (&v)[NV], double* scratch,
+                                                 double* history) {
+  __shared__ int s_last;
+  block_reduce<NV, THREADS>(v, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) ctx.partials[blockIdx.x * 4 + j] = v[j];
+    __threadfence();
+    const unsigned ticket = atomicAdd(ctx.counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double t[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) t[j] = 0.0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += THREADS)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) t[j] += __ldcg(ctx.partials + b * 4 + j);
+  block_reduce<NV, THREADS>(t, scratch);
+  if (threadIdx.x == 0) {
+    *ctx.counter = 0;
+    double r[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < NV; ++j) r[j] = t[j];
+    allreduce_ranks(ctx.comm, ctx.S, r, NV);
+    run_epilogue(ctx, r, history);
+    if (ctx.set_cond) cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(ctx.cond_handle), ctx.S->stop ? 0u : 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- staged CSR SpMV
+template <typename T>
+struct SpmvArgs {
+  const Tile* tiles;
+  int ntiles;
+  int first_boundary_tile;  // tiles [first_boundary_tile, ntiles) gather ghost entries
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const T* vals;
+  const T* x;       // extended vector [owned | ghost]
+  T* y;
+  const T* w;       // left operand of the first fused dot (nullptr: use x)
+  int stages, cap_nnz, cap_rows;
+  int tail_blk;     // float only: reference rounding pattern (0 = every product rounded)
+  int evict_first;  // stream the matrix through L2 with an evict-first policy
+  unsigned recv_mask;  // ranks whose halo must have arrived before boundary tiles (multi-GPU)
+  double* history;
+  RedCtx red;
+};
+
+template <typename T>
+__host__ __device__ inline size_t spmv_stage_bytes(int cap_nnz, int cap_rows) {
+  size_t v = (static_cast<size_t>(cap_nnz) + 16) * sizeof(T);
+  size_t c = (static_cast<size_t>(cap_nnz) + 8) * 4;
+  size_t r = (static_cast<size_t>(cap_rows) + 1 + 8) * 4;
+  auto up = [](size_t b) { return (b + 127) & ~static_cast<size_t>(127); };
+  return up(v) + up(c) + up(r);
+}
+
+template <typename T, int LG, bool STREAM>
+__device__ __forceinline__ void tile_rows_reduce(const T* __restrict__ sv, const int32_t* __restrict__ sc,
+                                                 const int32_t* __restrict__ srp, int nrows, int row0, int vb0,
+                                                 int cb0, const T* __restrict__ x, T* __restrict__ y,
+                                                 const T* __restrict__ w, int tail_blk, double& d0, double& d1) {
+  constexpr int L = 1 << LG;
+  const int lane = threadIdx.x & (L - 1);
+  const int grp = threadIdx.x >> LG;
+  constexpr int NGRP = kSpmvThreads >> LG;
+  for (int base = 0; base < nrows; base += NGRP) {
+    const int r = base + grp;
+    T sum = T(0);
+    if (r < nrows) {
+      int k = srp[r];
+      const int k1 = srp[r + 1];
+      if (L == 1) {
+        if (STREAM) {
+          for (; k < k1; ++k) sum = add_rn(sum, sv[k - vb0]);
+        } else {
+          const int kbody = (sizeof(T) == 4 && tail_blk > 0) ? k + ((k1 - k) / tail_blk) * tail_blk : k1;
+          for (; k + 4 <= kbody; k += 4) {
+            const int c0 = sc[k - cb0], c1 = sc[k + 1 - cb0], c2 = sc[k + 2 - cb0], c3 = sc[k + 3 - cb0];
+            const T x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+            sum = add_rn(sum, mul_rn(sv[k - vb0], x0));
+            sum = add_rn(sum, mul_rn(sv[k + 1 - vb0], x1));
+            sum = add_rn(sum, mul_rn(sv[k + 2 - vb0], x2));
+            sum = add_rn(sum, mul_rn(sv[k + 3 - vb0], x3));
+          }
+          for (; k < kbody; ++k) sum = add_rn(sum, mul_rn(sv[k - vb0], __ldg(x + sc[k - cb0])));
+          for (; k < k1; ++k) sum = fma_rn(sv[k - vb0], __ldg(x + sc[k - cb0]), sum);  // float epilogue pattern
+        }
+      } else {
+        for (k += lane; k < k1; k += L) {
+          if (STREAM)
+            sum = add_rn(sum, sv[k - vb0]);
+          else
+            sum = add_rn(sum, mul_rn(sv[k - vb0], __ldg(x + sc[k - cb0])));
+        }
+      }
+    }
+    if (L > 1) {
+#pragma unroll
+      for (int o = L / 2; o > 0; o >>= 1) sum = add_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+    }
+    if (r < nrows && lane == 0) {
+      sum = add_rn(sum, T(0));  // -0 -> +0, as `res += alpha*tmp` on a zeroed destination does
+      y[row0 + r] = sum;
+      if (w) d0 = fma_rn(static_cast<double>(w[row0 + r]), static_cast<double>(sum), d0);
+      d1 = fma_rn(static_cast<double>(sum), static_cast<double>(sum), d1);
+    }
+  }
+}
+
+template <typename T, int NDOT>
+__global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArgs<T> a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[8];
+  __shared__ double red_scratch[32 * 2];
+  __shared__ T long_scratch[32];
+  if (gated_out(a.red.S, a.red.gate)) return;
+
+  const int tid = threadIdx.x;
+  const size_t stage_bytes = spmv_stage_bytes<T>(a.cap_nnz, a.cap_rows);
+  const size_t v_bytes = ((static_cast<size_t>(a.cap_nnz) + 16) * sizeof(T) + 127) & ~static_cast<size_t>(127);
+  const size_t c_bytes = ((static_cast<size_t>(a.cap_nnz) + 8) * 4 + 127) & ~static_cast<size_t>(127);
+  constexpr int VA = 16 / sizeof(T);  // elements per 16-byte unit of the value array
+  const int S = a.stages;
+  const int G = gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint64_t policy = 0;
+  if (a.evict_first) policy = policy_evict_first();
+
+  auto issue = [&](int t, int s) {  // thread 0 only
+    const Tile tl = a.tiles[t];
+    uint64_t* bar = &full_bar[s];
+    if ((tl.meta >> 24) & kTileLong) { mbar_arrive(bar); return; }
+    const int nrows = tl.meta & 0xFFFF;
+    const int vb0 = tl.nnz0 & ~(VA - 1), vb1 = (tl.nnz0 + tl.nnz + VA - 1) & ~(VA - 1);
+    const int cb0 = tl.nnz0 & ~3, cb1 = (tl.nnz0 + tl.nnz + 3) & ~3;
+    const int rb0 = tl.row0 & ~3, rb1 = (tl.row0 + nrows + 1 + 3) & ~3;
+    const unsigned vby = static_cast<unsigned>(vb1 - vb0) * sizeof(T), cby = static_cast<unsigned>(cb1 - cb0) * 4u,
+                   rby = static_cast<unsigned>(rb1 - rb0) * 4u;
+    unsigned char* st = smem + static_cast<size_t>(s) * stage_bytes;
+    mbar_expect_tx(bar, vby + cby + rby);
+    if (a.evict_first) {
+      if (vby) bulk_g2s_hint(st, a.vals + vb0, vby, bar, policy);
+      if (cby) bulk_g2s_hint(st + v_bytes, a.colidx + cb0, cby, bar, policy);
+      bulk_g2s_hint(st + v_bytes + c_bytes, a.rowptr + rb0, rby, bar, policy);
+    } else {
+      if (vby) bulk_g2s(st, a.vals + vb0, vby, bar);
+      if (cby) bulk_g2s(st + v_bytes, a.colidx + cb0, cby, bar);
+      bulk_g2s(st + v_bytes + c_bytes, a.rowptr + rb0, rby, bar);
+    }
+  };
+
+  if (tid == 0)
+    for (int s = 0; s < S; ++s) {
+      const int t = blockIdx.x + s * G;
+      if (t < a.ntiles) issue(t, s);
+    }
+
+  double d0 = 0.0, d1 = 0.0;
+  const T* w = (NDOT >= 1) ? (a.w ? a.w : a.x) : nullptr;
+  bool halo_ready = (a.recv_mask == 0);
+
+  for (int it = 0;; ++it) {
+    const int t = blockIdx.x + it * G;
+    if (t >= a.ntiles) break;
+    const int s = it % S;
+    const unsigned parity = (it / S) & 1;
+    const Tile tl = a.tiles[t];
+    const int flags = (tl.meta >> 24) & 0xFF;
+    const int nrows = tl.meta & 0xFFFF;
+    const int lg = (tl.meta >> 16) & 0xFF;
+
+    if (!halo_ready && t >= a.first_boundary_tile) {  // ghost entries must have landed (multi-GPU)
+      if (tid == 0) {
+        const unsigned want = a.red.S->halo_seq;
+        for (int src = 0; src < a.red.comm.world; ++src)
+          if (a.recv_mask & (1u << src))
+            while (static_cast<int>(ld_acquire_sys(a.red.comm.halo_flag_self + src) - want) < 0) {
+            }
+      }
+      __syncthreads();
+      halo_ready = true;
+    }
+
+    mbar_wait(&full_bar[s], parity);
+
+    if (flags & kTileLong) {
+      // one row longer than a stage: the whole CTA streams it from global memory, coalesced
+      T sum = T(0);
+      const int k1 = tl.nnz0 + tl.nnz;
+      for (int k = tl.nnz0 + tid; k < k1; k += kSpmvThreads)
+        sum = add_rn(sum, mul_rn(a.vals[k], __ldg(a.x + a.colidx[k])));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum = add_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+      __syncthreads();
+      if ((tid & 31) == 0) long_scratch[tid >> 5] = sum;
+      __syncthreads();
+      if (tid < 32) {
+        sum = (tid < kSpmvThreads / 32) ? long_scratch[tid] : T(0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum = add_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+        if (tid == 0) {
+          sum = add_rn(sum, T(0));
+          a.y[tl.row0] = sum;
+          if (w) d0 = fma_rn(static_cast<double>(w[tl.row0]), static_cast<double>(sum), d0);
+          d1 = fma_rn(static_cast<double>(sum), static_cast<double>(sum), d1);
+        }
+      }
+    } else {
+      unsigned char* st = smem + static_cast<size_t>(s) * stage_bytes;
+      T* sv = reinterpret_cast<T*>(st);
+      const int32_t* sc = reinterpret_cast<const int32_t*>(st + v_bytes);
+      const int32_t* srp = reinterpret_cast<const int32_t*>(st + v_bytes + c_bytes) + (tl.row0 - (tl.row0 & ~3));
+      const int vb0 = tl.nnz0 & ~(VA - 1);
+      const int cb0 = tl.nnz0 & ~3;
+      if (flags & kTileStream) {
+        // phase 1: products, perfectly balanced over the CTA (CSR-stream); phase 2 sums them per row
+        const int k1 = tl.nnz0 + tl.nnz;
+        for (int k = tl.nnz0 + tid; k < k1; k += kSpmvThreads)
+          sv[k - vb0] = mul_rn(sv[k - vb0], __ldg(a.x + sc[k - cb0]));
+        __syncthreads();
+        switch (lg) {
+          case 0: tile_rows_reduce<T, 0, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 1: tile_rows_reduce<T, 1, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 2: tile_rows_reduce<T, 2, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 3: tile_rows_reduce<T, 3, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 4: tile_rows_reduce<T, 4, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          default: tile_rows_reduce<T, 5, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+        }
+      } else {
+        switch (lg) {
+          case 0: tile_rows_reduce<T, 0, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, a.tail_blk, d0, d1); break;
+          case 1: tile_rows_reduce<T, 1, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 2: tile_rows_reduce<T, 2, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 3: tile_rows_reduce<T, 3, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 4: tile_rows_reduce<T, 4, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          default: tile_rows_reduce<T, 5, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with stage s
+    if (tid == 0) {
+      const int t2 = t + S * G;
+      if (t2 < a.ntiles) issue(t2, s);
+    }
+  }
+
+  if (a.red.epilogue != kEpiNone) {
+    if (NDOT == 0) {
+      double v[1] = {0.0};
+      finish_reduction<1, kSpmvThreads>(a.red, v, red_scratch, a.history);
+    } else if (NDOT == 1) {
+      double v[1] = {d0};
+      finish_reduction<1, kSpmvThreads>(a.red, v, red_scratch, a.history);
+    } else {
+      double v[2] = {d0, d1};
+      finish_reduction<2, kSpmvThreads>(a.red, v, red_scratch, a.history);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- direct CSR SpMV
+// L = 2^LG lanes per row, straight from global memory; rows are dealt to lane groups in a fixed grid-stride order.
+template <typename T, int LG, int NDOT>
+__global__ void __launch_bounds__(kSpmvThreads) spmv_direct_kernel(const SpmvArgs<T> a, int rows) {
+  __shared__ double red_scratch[32 * 2];
+  if (gated_out(a.red.S, a.red.gate)) return;
+  constexpr int L = 1 << LG;
+  const int lane = threadIdx.x & (L - 1);
+  const long long grp0 = (static_cast<long long>(blockIdx.x) * kSpmvThreads + threadIdx.x) >> LG;
+  const long long ngrp = (static_cast<long long>(gridDim.x) * kSpmvThreads) >> LG;
+  const T* w = (NDOT >= 1) ? (a.w ? a.w : a.x) : nullptr;
+  double d0 = 0.0, d1 = 0.0;
+  if (a.recv_mask != 0) {  // direct kernel has no interior/boundary split: wait for the halo up front
+    if (threadIdx.x == 0) {
+      const unsigned want = a.red.S->halo_seq;
+      for (int src = 0; src < a.red.comm.world; ++src)
+        if (a.recv_mask & (1u << src))
+          while (static_cast<int>(ld_acquire_sys(a.red.comm.halo_flag_self + src) - want) < 0) {
+          }
+    }
+    __syncthreads();
+  }
+  for (long long base = 0; base < rows; base += ngrp) {
+    const long long r = base + grp0;
+    T sum = T(0);
+    if (r < rows) {
+      const int k1 = a.rowptr[r + 1];
+      for (int k = a.rowptr[r] + lane; k < k1; k += L) sum = add_rn(sum, mul_rn(a.vals[k], __ldg(a.x + a.colidx[k])));
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) sum = add_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+    if (r < rows && lane == 0) {
+      sum = add_rn(sum, T(0));
+      a.y[r] = sum;
+      if (w) d0 = fma_rn(static_cast<double>(w[r]), static_cast<double>(sum), d0);
+      d1 = fma_rn(static_cast<double>(sum), static_cast<double>(sum), d1);
+    }
+  }
+  if (a.red.epilogue != kEpiNone) {
+    if (NDOT <= 1) {
+      double v[1] = {NDOT ? d0 : 0.0};
+      finish_reduction<1, kSpmvThreads>(a.red, v, red_scratch, a.history);
+    } else {
+      double v[2] = {d0, d1};
+      finish_reduction<2, kSpmvThreads>(a.red, v, red_scratch, a.history);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Jacobi setup
+// BasicPreconditioners.h:64-79: first stored entry with inner index == j; missing or zero -> 1.
+template <typename T>
+__global__ void jacobi_factorize_kernel(int rows, const int32_t* __restrict__ rowptr,
+                                        const int32_t* __restrict__ colidx, const T* __restrict__ vals,
+                                        T* __restrict__ invdiag, int identity) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= rows) return;
+  T d = T(1);
+  if (!identity) {
+    int k = rowptr[j];
+    const int e = rowptr[j + 1];
+    while (k < e && colidx[k] != j) ++k;
+    if (k < e && vals[k] != T(0)) d = T(1) / vals[k];
+  }
+  invdiag[j] = d;
+}
+
+// vals_out[k] = vals_in[src[k]]  (uncompressed input / symmetric expansion)
+template <typename T>
+__global__ void gather_values_kernel(long long n, const int32_t* __restrict__ src, const T* __restrict__ in,
+                                     T* __restrict__ out) {
+  for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[k] = in[src[k]];
+}
+
+// ------------------------------------------------------------------------------------------ fused vector passes
+struct VecArgs {
+  long long n;
+  double* x;
+  double* r;
+  double* p;
+  double* q;        // Ap (CG) / v (BiCGSTAB)
+  double* y;
+  double* z;
+  double* s;
+  double* t;
+  double* r0;
+  const double* b;
+  const double* invdiag;
+  double* history;
+  RedCtx red;
+};
+
+// Elements are dealt to threads in pairs (128-bit accesses) in a fixed grid-stride order; an odd tail element is
+// taken by thread 0 of CTA 0.  f2(i2) handles elements 2*i2 and 2*i2+1, f1(i) a single element.
+template <typename F2, typename F1>
+__device__ __forceinline__ void vec_loop(long long n, F2 f2, F1 f1) {
+  const long long n2 = n >> 1;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i2 < n2; i2 += stride) f2(i2);
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) f1(n - 1);
+}
+
+__device__ __forceinline__ double2 ld2(const double* p, long long i2) { return reinterpret_cast<const double2*>(p)[i2]; }
+__device__ __forceinline__ void st2(double* p, long long i2, double2 v) { reinterpret_cast<double2*>(p)[i2] = v; }
+
+// CG start (ConjugateGradient.h:43-67): r = b - A x0 (q holds A x0 when there is a guess, else r = b),
+// p = D^-1 r, and the three reductions ||b||^2, ||r||^2, r.p in the same pass.
+__global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const VecArgs a) {
+  __shared__ double scratch[32 * 3];
+  const bool guess = a.red.S->use_guess != 0;
+  double v[3] = {0.0, 0.0, 0.0};
+  vec_loop(a.n,
+    [&](long long i2) {
+      const double2 b = ld2(a.b, i2), d = ld2(a.invdiag, i2);
+      double2 r = b;
+      if (guess) { const double2 q = ld2(a.q, i2); r.x = b.x - q.x; r.y = b.y - q.y; }
+      else st2(a.x, i2, make_double2(0.0, 0.0));  // solve() starts from x = 0 (IterativeSolverBase.h:402)
+      double2 p; p.x = d.x * r.x; p.y = d.y * r.y;
+      st2(a.r, i2, r); st2(a.p, i2, p);
+      v[0] = fma_rn(b.x, b.x, v[0]); v[0] = fma_rn(b.y, b.y, v[0]);
+      v[1] = fma_rn(r.x, r.x, v[1]); v[1] = fma_rn(r.y, r.y, v[1]);
+      v[2] = fma_rn(r.x, p.x, v[2]); v[2] = fma_rn(r.y, p.y, v[2]);
+    },
+    [&](long long i) {
+      const double b = a.b[i];
+      const double r = guess ? b - a.q[i] : b;
+      if (!guess) a.x[i] = 0.0;
+      const double p = a.invdiag[i] * r;
+      a.r[i] = r; a.p[i] = p;
+      v[0] = fma_rn(b, b, v[0]); v[1] = fma_rn(r, r, v[1]); v[2] = fma_rn(r, p, v[2]);
+    });
+  finish_reduction<3, kVecThreads>(a.red, v, scratch, a.history);
+}
+
+// CG :74-84 in one pass: x += alpha p; r -= alpha Ap; z = D^-1 r (not stored); ||r||^2; r.z
+__global__ void __launch_bounds__(kVecThreads) cg_update_kernel(const VecArgs a) {
+  __shared__ double scratch[32 * 2];
+  if (gated_out(a.red.S, a.red.gate)) return;
+  const double alpha = a.red.S->alpha;
+  double v[2] = {0.0, 0.0};
+  vec_loop(a.n,
+    [&](long long i2) {
+      double2 x = ld2(a.x, i2), r = ld2(a.r, i2);
+      const double2 p = ld2(a.p, i2), q = ld2(a.q, i2), d = ld2(a.invdiag, i2);
+      x.x = fma_rn(alpha, p.x, x.x); x.y = fma_rn(alpha, p.y, x.y);
+      r.x = fma_rn(-alpha, q.x, r.x); r.y = fma_rn(-alpha, q.y, r.y);
+      st2(a.x, i2, x); st2(a.r, i2, r);
+      const double zx = d.x * r.x, zy = d.y * r.y;
+      v[0] = fma_rn(r.x, r.x, v[0]); v[0] = fma_rn(r.y, r.y, v[0]);
+      v[1] = fma_rn(r.x, zx, v[1]); v[1] = fma_rn(r.y, zy, v[1]);
+    },
+    [&](long long i) {
+      const double x = fma_rn(alpha, a.p[i], a.x[i]);
+      const double r = fma_rn(-alpha, a.q[i], a.r[i]);
+      a.x[i] = x; a.r[i] = r;
+      const double z = a.invdiag[i] * r;
+      v[0] = fma_rn(r, r, v[0]); v[1] = fma_rn(r, z, v[1]);
+    });
+  finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
+}
+
+// CG :81,:86: p = D^-1 r + beta p
+__global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgs a) {
+  if (gated_out(a.red.S, a.red.gate)) return;
+  const double beta = a.red.S->beta;
+  vec_loop(a.n,
+    [&](long long i2) {
+      const double2 r = ld2(a.r, i2), d = ld2(a.invdiag, i2);
+      double2 p = ld2(a.p, i2);
+      p.x = fma_rn(beta, p.x, d.x * r.x); p.y = fma_rn(beta, p.y, d.y * r.y);
+      st2(a.p, i2, p);
+    },
+    [&](long long i) { a.p[i] = fma_rn(beta, a.p[i], a.invdiag[i] * a.r[i]); });
+}
+
+// BiCGSTAB start (BiCGSTAB.h:42-46): r = b - A x0 (t holds A x0), r0 = r, ||b||^2, ||r||^2; v = p = 0 (:56)
+__global__ void __launch_bounds__(kVecThreads) bicg_init_kernel(const VecArgs a) {
+  __shared__ double scratch[32 * 2];
+  const bool guess = a.red.S->use_guess != 0;
+  double v[2] = {0.0, 0.0};
+  vec_loop(a.n,
+    [&](long long i2) {
+      const double2 b = ld2(a.b, i2);
+      double2 r = b;
+      if (guess) { const double2 t = ld2(a.t, i2); r.x = b.x - t.x; r.y = b.y - t.y; }
+      else st2(a.x, i2, make_double2(0.0, 0.0));
+      st2(a.r, i2, r); st2(a.r0, i2, r);
+      st2(a.q, i2, make_double2(0.0, 0.0)); st2(a.p, i2, make_double2(0.0, 0.0));
+      v[0] = fma_rn(b.x, b.x, v[0]); v[0] = fma_rn(b.y, b.y, v[0]);
+      v[1] = fma_rn(r.x, r.x, v[1]); v[1] = fma_rn(r.y, r.y, v[1]);
+    },
+    [&](long long i) {
+      const double b = a.b[i];
+      const double r = guess ? b - a.t[i] : b;
+      if (!guess) a.x[i] = 0.0;
+      a.r[i] = r; a.r0[i] = r; a.q[i] = 0.0; a.p[i] = 0.0;
+      v[0] = fma_rn(b, b, v[0]); v[1] = fma_rn(r, r, v[1]);
+    });
+  finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
+}
+
+// BiCGSTAB restart (:75-77): r = b - A x (t holds A x), r0 = r, ||r||^2
+__global__ void __launch_bounds__(kVecThreads) bicg_restart_kernel(const VecArgs a) {
+  __shared__ double scratch[32];
+  if (gated_out(a.red.S, a.red.gate)) return;
+  double v[1] = {0.0};
+  vec_loop(a.n,
+    [&](long long i2) {
+      const double2 b = ld2(a.b, i2), t = ld2(a.t, i2);
+      double2 r; r.x = b.x - t.x; r.y = b.y - t.y;
+      st2(a.r, i2, r); st2(a.r0, i2, r);
+      v[0] = fma_rn(r.x, r.x, v[0]); v[0] = fma_rn(r.y, r.y, v[0]);
+    },
+    [&](long long i) {
+      const double r = a.b[i] - a.t[i];
+      a.r[i] = r; a.r0[i] = r;
+      v[0] = fma_rn(r, r, v[0]);
+    });
+  finish_reduction<1, kVecThreads>(a.red, v, scratch, a.history);
+}
+
+// BiCGSTAB :82-85: beta = (rho/rho_old)(alpha/w); p = r + beta (p - w v); y = D^-1 p
+__global__ void __launch_bounds__(kVecThreads) bicg_p_kernel(const VecArgs a) {
+  if (gated_out(a.red.S, a.red.gate)) return;
+  const Scalars* S = a.red.S;
+  const double beta = (S->rho / S->rho_old) * (S->alpha / S->w);
+  const double w = S->w;
+  vec_loop(a.n,
+    [&](long long i2) {
+      const double2 r = ld2(a.r, i2), vv = ld2(a.q, i2), d = ld2(a.invdiag, i2);
+      double2 p = ld2(a.p, i2);
+      p.x = fma_rn(beta, fma_rn(-w, vv.x, p.x), r.x); p.y = fma_rn(beta, fma_rn(-w, vv.y, p.y), r.y);
+      st2(a.p, i2, p);
+      st2(a.y, i2, make_double2(d.x * p.x, d.y * p.y));
+    },
+    [&](long long i) {
+      const double p = fma_rn(beta, fma_rn(-w, a.q[i], a.p[i]), a.r[i]);
+      a.p[i] = p; a.y[i] = a.invdiag[i] * p;
+    });
+}
+
+// BiCGSTAB :90-92: s = r - alpha v; z = D^-1 s
+__global__ void __launch_bounds__(kVecThreads) bicg_s_kernel(const VecArgs a) {
+  if (gated_out(a.red.S, a.red.gate)) return;
+  const double alpha = a.red.S->alpha;
+  vec_loop(a.n,
+    [&](long long i2) {
+      const double2 r = ld2(a.r, i2), vv = ld2(a.q, i2), d = ld2(a.invdiag, i2);
+      double2 s; s.x = fma_rn(-alpha, vv.x, r.x); s.y = fma_rn(-alpha, vv.y, r.y);
+      st2(a.s, i2, s);
+      st2(a.z, i2, make_double2(d.x * s.x, d.y * s.y));
+    },
+    [&](long long i) {
+      const double s = fma_rn(-alpha, a.q[i], a.r[i]);
+      a.s[i] = s; a.z[i] = a.invdiag[i] * s;
+    });
+}
+
+// BiCGSTAB :100-101 and the next loop head :67,:71: x += alpha y + w z; r = s - w t; ||r||^2; r0.r
+__global__ void __launch_bounds__(kVecThreads) bicg_update_kernel(const VecArgs a) {
+  __shared__ double scratch[32 * 2];
+  if (gated_out(a.red.S, a.red.gate)) return;
+  const double alpha = a.red.S->alpha, w = a.red.S->w;
+  double v[2] = {0.0, 0.0};
+  vec_loop(a.n,
+    [&](long long i2) {
+      double2 x = ld2(a.x, i2);
+      const double2 y = ld2(a.y, i2), z = ld2(a.z, i2), s = ld2(a.s, i2), t = ld2(a.t, i2), r0 = ld2(a.r0, i2);
+      x.x = x.x + fma_rn(w, z.x, alpha * y.x); x.y = x.y + fma_rn(w, z.y, alpha * y.y);
+      double2 r; r.x = fma_rn(-w, t.x, s.x); r.y = fma_rn(-w, t.y, s.y);
+      st2(a.x, i2, x); st2(a.r, i2, r);
+      v[0] = fma_rn(r.x, r.x, v[0]); v[0] = fma_rn(r.y, r.y, v[0]);
+      v[1] = fma_rn(r0.x, r.x, v[1]); v[1] = fma_rn(r0.y, r.y, v[1]);
+    },
+    [&](long long i) {
+      const double x = a.x[i] + fma_rn(w, a.z[i], alpha * a.y[i]);
+      const double r = fma_rn(-w, a.t[i], a.s[i]);
+      a.x[i] = x; a.r[i] = r;
+      v[0] = fma_rn(r, r, v[0]); v[1] = fma_rn(a.r0[i], r, v[1]);
+    });
+  finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
+}
+
+// x = 0 when ||b|| == 0 (ConjugateGradient.h:48, BiCGSTAB.h:49); otherwise nothing.
+__global__ void __launch_bounds__(kVecThreads) finalize_kernel(const VecArgs a) {
+  if (!a.red.S->rhs_zero) return;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    a.x[i] = 0.0;
+}
+
+// Sets the WHILE condition from the control state (used after the init phase and by chunk boundaries).
+__global__ void set_condition_kernel(const Scalars* S, unsigned long long handle) {
+  cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(handle), S->stop ? 0u : 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------- halo push
+template <typename T>
+struct HaloArgs {
+  const T* x;                 // owned entries of the vector being exchanged
+  const int32_t* send_rows;   // grouped by destination
+  long long send_offsets[kMaxWorld];
+  long long send_counts[kMaxWorld];
+  T* dst[kMaxWorld];          // peer's ghost slots for my entries (NVLink-mapped)
+  unsigned int* counter;
+  RedCtx red;                 // S, gate, comm
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) halo_push_kernel(const HaloArgs<T> a) {
+  __shared__ int s_last;
+  if (gated_out(a.red.S, a.red.gate)) return;
+  const CommDev& c = a.red.comm;
+  for (int q = 0; q < c.world; ++q) {
+    const long long n = a.send_counts[q];
+    const int32_t* rows = a.send_rows + a.send_offsets[q];
+    T* dst = a.dst[q];
+    for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < n;
+         k += static_cast<long long>(gridDim.x) * blockDim.x)
+      dst[k] = a.x[rows[k]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(a.counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    *a.counter = 0;
+    __threadfence_system();
+    const unsigned seq = ++a.red.S->halo_seq;
+    for (int q = 0; q < c.world; ++q)
+      if (a.send_counts[q] > 0) st_release_sys(c.halo_flag_peer[q] + c.rank, seq);
+  }
+}
+
+}  // namespace b200s

@@ -1,0 +1,359 @@
+"""Host-side mirror of the reference's solver interface for the B200 path.
+
+``ConjugateGradient`` and ``BiCGSTAB`` keep the names, argument meaning and error behaviour of
+/root/reference/Eigen/src/IterativeLinearSolvers/IterativeSolverBase.h:142-440 (compute / analyzePattern / factorize /
+solve / solveWithGuess / setTolerance / tolerance / setMaxIterations / maxIterations / iterations / error / info) and
+of ConjugateGradient.h:157-225 / BiCGSTAB.h:157-208, and forward to the C ABI of include/b200sparse.h.  The C++
+counterpart for Eigen users is include/b200/IterativeSolvers.h.  There is no CPU path: everything numeric happens in
+libb200sparse.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200Error, Config, Stats
+from .workloads import CsrMatrix
+
+# Eigen's enums (Core/util/Constants.h)
+Lower, Upper = 1, 2
+Success, NumericalIssue, NoConvergence, InvalidInput = 0, 1, 2, 3
+IdentityPreconditioner, DiagonalPreconditioner = 0, 1
+
+SPMV_AUTO, SPMV_STAGED, SPMV_DIRECT = 0, 1, 2
+LOOP_AUTO, LOOP_WHILE_GRAPH, LOOP_CHUNKED_GRAPH, LOOP_STREAM = 0, 1, 2, 3
+
+
+def device_count() -> int:
+    return _lib.lib().b200s_device_count()
+
+
+def _ptr(a) -> C.c_void_p:
+    """Pointer of a numpy array, a torch tensor (data_ptr) or a raw integer address."""
+    if a is None:
+        return C.c_void_p(None)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+def _as_csr(A) -> CsrMatrix:
+    if isinstance(A, CsrMatrix):
+        return A
+    if hasattr(A, "indptr"):  # scipy.sparse
+        A = A.tocsr()
+        return CsrMatrix(A.shape[0], A.shape[1], np.ascontiguousarray(A.indptr, np.int32),
+                         np.ascontiguousarray(A.indices, np.int32), np.ascontiguousarray(A.data), 0)
+    raise TypeError("expected a CsrMatrix or a scipy.sparse matrix")
+
+
+class Communicator:
+    """Row-block partition context of one process per GPU.  ``allgather(bytes) -> list[bytes]`` is only used while
+    the plan is built (setup); the iteration itself talks over NVLink peer memory."""
+
+    def __init__(self, rank: int, world: int, allgather, row_starts):
+        self.rank, self.world = int(rank), int(world)
+        self._allgather = allgather
+        self.row_starts = np.ascontiguousarray(row_starts, dtype=np.int64)
+        assert self.row_starts.shape[0] == self.world + 1
+        self.errors = []
+
+        def cb(_ctx, send, recv, nbytes):
+            try:
+                mine = C.string_at(send, nbytes)
+                parts = self._allgather(mine)
+                assert len(parts) == self.world and all(len(p) == nbytes for p in parts)
+                C.memmove(recv, b"".join(parts), nbytes * self.world)
+                return 0
+            except Exception as e:  # never let an exception cross the C boundary
+                self.errors.append(e)
+                return 1
+
+        self.callback = _lib.ALLGATHER_FN(cb)
+
+    @staticmethod
+    def from_torch(row_starts, group=None):
+        """Bootstrap over torch.distributed (a gloo group; with an NCCL default group pass a gloo subgroup)."""
+        import torch
+        import torch.distributed as dist
+
+        def allgather(b: bytes):
+            t = torch.frombuffer(bytearray(b), dtype=torch.uint8)
+            out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+            dist.all_gather(out, t, group=group)
+            return [bytes(o.numpy().tobytes()) for o in out]
+
+        return Communicator(dist.get_rank(group), dist.get_world_size(group), allgather, row_starts)
+
+
+def partition_rows(n: int, world: int, align: int = 1) -> np.ndarray:
+    """Contiguous, balanced row blocks; ``align`` keeps block edges on grid-plane boundaries."""
+    units = n // align
+    starts = [(units * r // world) * align for r in range(world)] + [n]
+    return np.asarray(starts, dtype=np.int64)
+
+
+class _Handle:
+    """Owns one b200s_handle."""
+
+    def __init__(self, comm: Optional[Communicator] = None, device: int = -1, spmv_impl: int = 0, loop_mode: int = 0,
+                 chunk_iters: int = 0, tile_nnz: int = 0, tile_rows: int = 0):
+        self.L = _lib.lib()
+        self.comm = comm
+        cfg = Config()
+        cfg.struct_size = C.sizeof(Config)
+        cfg.device = device
+        cfg.rank = comm.rank if comm else 0
+        cfg.world = comm.world if comm else 1
+        cfg.spmv_impl, cfg.loop_mode, cfg.chunk_iters = spmv_impl, loop_mode, chunk_iters
+        cfg.tile_nnz, cfg.tile_rows = tile_nnz, tile_rows
+        if comm:
+            cfg.allgather = comm.callback
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.L.b200s_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise B200Error(rc, self.L.b200s_last_error(None).decode())
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.L.b200s_last_error(self.h).decode()
+            if self.comm and self.comm.errors:
+                msg += f" (allgather callback: {self.comm.errors[-1]!r})"
+            raise B200Error(rc, msg)
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.b200s_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self) -> dict:
+        st = Stats()
+        st.struct_size = C.sizeof(Stats)
+        self.check(self.L.b200s_get_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+
+class SparseOperator:
+    """``y = A * x`` on the GPU: the product of SparseDenseProduct.h:26-72 for a row-major matrix."""
+
+    def __init__(self, A=None, uplo: int = Lower | Upper, comm: Optional[Communicator] = None, **cfg):
+        self._hd = _Handle(comm, **cfg)
+        self._comm = comm
+        self._uplo = uplo
+        self._dtype = None
+        self._rows = self._cols = 0
+        if A is not None:
+            self.compute(A)
+
+    def analyzePattern(self, A, inner_nnz=None):
+        A = _as_csr(A)
+        self._rows, self._cols = A.rows, A.cols
+        rs = self._comm.row_starts if self._comm else None
+        inz = None if inner_nnz is None else np.ascontiguousarray(inner_nnz, np.int32)
+        self._keep = (A.rowptr, A.colidx, inz, rs)
+        nnz = int(A.colidx.shape[0])
+        self._hd.check(self._hd.L.b200s_analyze_pattern(self._hd.h, A.rows, A.cols, nnz, _ptr(A.rowptr), _ptr(A.colidx),
+                                                        _ptr(inz), self._uplo, _ptr(rs)))
+        return self
+
+    def factorize(self, A, precond: int = DiagonalPreconditioner):
+        A = _as_csr(A)
+        vals = np.ascontiguousarray(A.vals)
+        if vals.dtype == np.float32:
+            self._hd.check(self._hd.L.b200s_factorize_f32(self._hd.h, _ptr(vals), precond))
+        elif vals.dtype == np.float64:
+            self._hd.check(self._hd.L.b200s_factorize_f64(self._hd.h, _ptr(vals), precond))
+        else:
+            raise TypeError("values must be float32 or float64")
+        self._dtype = vals.dtype
+        return self
+
+    def compute(self, A, precond: int = DiagonalPreconditioner, inner_nnz=None):
+        return self.analyzePattern(A, inner_nnz).factorize(A, precond)
+
+    def rows(self):
+        return self._rows
+
+    def cols(self):
+        return self._cols
+
+    def multiply(self, x: np.ndarray) -> np.ndarray:
+        """Host vectors in, host vector out (H2D + kernel + D2H)."""
+        x = np.ascontiguousarray(x, dtype=self._dtype)
+        nx = self._cols if not self._comm or self._comm.world == 1 else self._rows
+        if x.shape != (nx,):
+            raise ValueError(f"x must have shape ({nx},)")
+        y = np.empty(self._rows, dtype=self._dtype)
+        fn = self._hd.L.b200s_spmv_f32 if self._dtype == np.float32 else self._hd.L.b200s_spmv_f64
+        self._hd.check(fn(self._hd.h, _ptr(x), _ptr(y)))
+        return y
+
+    __matmul__ = multiply
+
+    def multiply_device(self, x_dev, y_dev, reps: int = 1) -> float:
+        """Device pointers (torch tensors or addresses); returns the average kernel time in ms."""
+        ms = C.c_float(0)
+        fn = self._hd.L.b200s_spmv_device_f32 if self._dtype == np.float32 else self._hd.L.b200s_spmv_device_f64
+        self._hd.check(fn(self._hd.h, _ptr(x_dev), _ptr(y_dev), reps, C.byref(ms)))
+        return ms.value
+
+    def invdiag(self) -> np.ndarray:
+        d = np.empty(self._rows, dtype=np.float64)
+        self._hd.check(self._hd.L.b200s_get_invdiag_f64(self._hd.h, _ptr(d)))
+        return d
+
+    def stats(self) -> dict:
+        return self._hd.stats()
+
+    def close(self):
+        self._hd.close()
+
+
+class _IterativeSolverBase(SparseOperator):
+    """IterativeSolverBase.h:142-440."""
+
+    _bicg = False
+
+    def __init__(self, A=None, uplo: int = Lower | Upper, preconditioner: int = DiagonalPreconditioner,
+                 comm: Optional[Communicator] = None, **cfg):
+        self._precond = preconditioner
+        self._tolerance = float(np.finfo(np.float64).eps)  # :413
+        self._max_iterations = -1                            # :281-284 -> 2*cols
+        self._iterations = 0
+        self._error = 0.0
+        self._info = Success
+        self._is_initialized = False
+        super().__init__(None, uplo, comm, **cfg)
+        if A is not None:
+            self.compute(A)
+
+    # ---- setup (IterativeSolverBase.h:196-247) ----
+    def analyzePattern(self, A, inner_nnz=None):
+        super().analyzePattern(A, inner_nnz)
+        self._analysis_ok = True
+        self._is_initialized = True
+        self._info = Success
+        return self
+
+    def factorize(self, A, precond=None):
+        if not getattr(self, "_analysis_ok", False):
+            raise AssertionError("You must first call analyzePattern()")  # :218
+        super().factorize(A, self._precond if precond is None else precond)
+        self._factorization_ok = True
+        self._info = Success
+        return self
+
+    def compute(self, A, precond=None, inner_nnz=None):
+        self.analyzePattern(A, inner_nnz)
+        return self.factorize(A, precond)
+
+    # ---- parameters (:258-293) ----
+    def tolerance(self):
+        return self._tolerance
+
+    def setTolerance(self, tol):
+        self._tolerance = float(tol)
+        return self
+
+    def maxIterations(self):
+        return 2 * self._cols if self._max_iterations < 0 else self._max_iterations
+
+    def setMaxIterations(self, n):
+        self._max_iterations = int(n)
+        return self
+
+    # ---- results (:296-330) ----
+    def iterations(self):
+        if not self._is_initialized:
+            raise AssertionError("ConjugateGradient is not initialized.")
+        return self._iterations
+
+    def error(self):
+        if not self._is_initialized:
+            raise AssertionError("ConjugateGradient is not initialized.")
+        return self._error
+
+    def info(self):
+        if not self._is_initialized:
+            raise AssertionError("IterativeSolverBase is not initialized.")
+        return self._info
+
+    # ---- solves (:316-323, :333-404) ----
+    def _solve_vector(self, b: np.ndarray, x: np.ndarray, use_guess: bool):
+        it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
+        fn = self._hd.L.b200s_bicgstab_solve_f64 if self._bicg else self._hd.L.b200s_cg_solve_f64
+        self._hd.check(fn(self._hd.h, _ptr(b), _ptr(x), int(use_guess), self._tolerance, self.maxIterations(),
+                          C.byref(it), C.byref(err), C.byref(info)))
+        return it.value, err.value, info.value
+
+    def _solve(self, b, x0):
+        if not self._is_initialized:
+            raise AssertionError("solver is not initialized.")  # :337
+        b = np.asarray(b, dtype=np.float64)
+        if b.shape[0] != self._rows:
+            raise AssertionError("solve(): invalid number of rows of the right hand side matrix b")
+        if b.ndim == 1:
+            x = np.zeros(self._rows) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+            self._iterations, self._error, self._info = self._solve_vector(np.ascontiguousarray(b), x, x0 is not None)
+            return x
+        # multi-column right-hand side: sequential, info = worst, iterations / error = last column (:375-388)
+        X = np.zeros(b.shape, order="F") if x0 is None else np.array(x0, dtype=np.float64, order="F", copy=True)
+        global_info = Success
+        for k in range(b.shape[1]):
+            xk = np.ascontiguousarray(X[:, k])
+            self._iterations, self._error, info = self._solve_vector(np.ascontiguousarray(b[:, k]), xk, x0 is not None)
+            X[:, k] = xk
+            if info == NumericalIssue:
+                global_info = NumericalIssue
+            elif info == NoConvergence and global_info != NumericalIssue:
+                global_info = NoConvergence
+        self._info = global_info
+        return X
+
+    def solve(self, b):
+        return self._solve(b, None)
+
+    def solveWithGuess(self, b, x0):
+        return self._solve(b, x0)
+
+    def solve_device(self, b_dev, x_dev, use_guess: bool = False):
+        """Inputs resident in HBM (torch tensors / device addresses of this rank's rows)."""
+        it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
+        fn = self._hd.L.b200s_bicgstab_solve_device_f64 if self._bicg else self._hd.L.b200s_cg_solve_device_f64
+        self._hd.check(fn(self._hd.h, _ptr(b_dev), _ptr(x_dev), int(use_guess), self._tolerance, self.maxIterations(),
+                          C.byref(it), C.byref(err), C.byref(info)))
+        self._iterations, self._error, self._info = it.value, err.value, info.value
+        return x_dev
+
+    def residual_history(self, cap: int = 1 << 16) -> np.ndarray:
+        rr = np.empty(cap, dtype=np.float64)
+        n = self._hd.L.b200s_get_residual_history(self._hd.h, _ptr(rr), cap)
+        if n < 0:
+            self._hd.check(int(n))
+        return rr[:n].copy()
+
+
+class ConjugateGradient(_IterativeSolverBase):
+    """ConjugateGradient<SparseMatrix<double,RowMajor>, UpLo, Preconditioner> (ConjugateGradient.h:157-225)."""
+    _bicg = False
+
+
+class BiCGSTAB(_IterativeSolverBase):
+    """BiCGSTAB<SparseMatrix<double,RowMajor>, Preconditioner> (BiCGSTAB.h:157-208); the matrix is used as stored."""
+    _bicg = True
+
+    def __init__(self, A=None, preconditioner: int = DiagonalPreconditioner, comm: Optional[Communicator] = None,
+                 **cfg):
+        super().__init__(A, Lower | Upper, preconditioner, comm, **cfg)

@@ -1,0 +1,169 @@
+/* b200sparse.h -- C ABI of the B200-native sparse iterative-solve hot path.
+ *
+ * This library replaces, on one or more NVIDIA B200 GPUs (sm_100a), exactly one path of Eigen
+ * (paths relative to the reference tree):
+ *
+ *   y = A*x, CSR                    Eigen/src/SparseCore/SparseDenseProduct.h:26-72
+ *   ConjugateGradient loop          Eigen/src/IterativeLinearSolvers/ConjugateGradient.h:26-91, :197-221
+ *   BiCGSTAB loop                   Eigen/src/IterativeLinearSolvers/BiCGSTAB.h:28-107, :193-204
+ *   Jacobi / identity precond.      Eigen/src/IterativeLinearSolvers/BasicPreconditioners.h:64-101, :200-222
+ *   solver state and setters        Eigen/src/IterativeLinearSolvers/IterativeSolverBase.h:196-330, :399-413
+ *
+ * Eigen has no FFI; the reference-side binding is the CRTP solver concept (IterativeSolverBase<Derived>), in the
+ * manner of Eigen/src/KLUSupport/KLUSupport.h:60-115.  include/b200/IterativeSolvers.h is that binding (C++,
+ * header-only, needs Eigen); INTEGRATION.md shows it.  Python tests and bench.py bind the same symbols via ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative b200s_status; b200s_last_error() gives the text.
+ *     No exceptions cross the boundary.  A handle is not re-entrant; distinct handles are independent.
+ *   - host arrays are BORROWED for the duration of the call and copied to the device; nothing is retained.
+ *   - "_device" variants take device pointers (valid on the handle's device) and never touch host memory.
+ *   - there is NO CPU fallback: without a usable sm_100 device b200s_create fails with B200S_ERR_NO_DEVICE.
+ *   - indices are int32 (Eigen's default StorageIndex, SparseMatrix.h:36); sizes are int64.
+ *   - uplo uses Eigen's bit values (Core/util/Constants.h): 1 = Lower, 2 = Upper, 3 = Lower|Upper.
+ *   - info uses Eigen's ComputationInfo (Core/util/Constants.h:430-440): 0 Success, 1 NumericalIssue,
+ *     2 NoConvergence, 3 InvalidInput.
+ */
+#ifndef B200SPARSE_H
+#define B200SPARSE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200S_VERSION 100
+
+typedef struct b200s_handle b200s_handle;
+
+typedef enum {
+  B200S_OK = 0,
+  B200S_ERR_INVALID = -1,   /* bad argument / call order (Eigen: eigen_assert or InvalidInput) */
+  B200S_ERR_NO_DEVICE = -2, /* no CUDA device of compute capability 10.x: the product has no CPU path */
+  B200S_ERR_CUDA = -3,      /* a CUDA runtime call failed; text in b200s_last_error */
+  B200S_ERR_ALLOC = -4,
+  B200S_ERR_COMM = -5,      /* multi-GPU bootstrap failed */
+  B200S_ERR_UNSUPPORTED = -6
+} b200s_status;
+
+enum { B200S_LOWER = 1, B200S_UPPER = 2, B200S_BOTH = 3 };
+enum { B200S_PRECOND_IDENTITY = 0, B200S_PRECOND_JACOBI = 1 };
+enum { B200S_SPMV_AUTO = 0, B200S_SPMV_STAGED = 1, B200S_SPMV_DIRECT = 2 };
+enum { B200S_LOOP_AUTO = 0, B200S_LOOP_WHILE_GRAPH = 1, B200S_LOOP_CHUNKED_GRAPH = 2, B200S_LOOP_STREAM = 3 };
+
+/* Host-provided all-gather used ONLY while building the multi-GPU plan (setup, never in the iteration):
+ * every rank contributes `bytes` bytes from `send`; `recv` receives world*bytes, ordered by rank.  Return 0 on
+ * success.  Python binds it to torch.distributed.all_gather, C++ hosts to MPI_Allgather. */
+typedef int (*b200s_allgather_fn)(void* ctx, const void* send, void* recv, size_t bytes);
+
+typedef struct {
+  int32_t struct_size;  /* = sizeof(b200s_config); lets the struct grow */
+  int32_t device;       /* CUDA device ordinal; -1 = current device */
+  int32_t rank;         /* this process owns row block `rank` of `world` (one process per GPU) */
+  int32_t world;        /* 1 = single GPU */
+  int32_t spmv_impl;    /* B200S_SPMV_* */
+  int32_t loop_mode;    /* B200S_LOOP_* */
+  int32_t chunk_iters;  /* iterations per graph launch in CHUNKED mode (0 = default 32) */
+  int32_t tile_nnz;     /* staged SpMV: max non-zeros per shared-memory tile (0 = default) */
+  int32_t tile_rows;    /* staged SpMV: max rows per tile (0 = default) */
+  int32_t reserved0;
+  b200s_allgather_fn allgather; /* required when world > 1 */
+  void* allgather_ctx;
+} b200s_config;
+
+typedef struct {
+  int32_t struct_size;
+  int32_t world, rank, device;
+  int64_t rows, cols, nnz;          /* local block after compression / symmetric expansion */
+  int64_t ghosts;                   /* halo entries received per SpMV */
+  int64_t halo_send;                /* halo entries sent per SpMV */
+  int32_t tiles, tiles_boundary;    /* staged-SpMV tiles (total / touching ghosts) */
+  int32_t tiles_by_lanes[6];        /* tiles using 1,2,4,8,16,32 lanes per row */
+  int32_t tiles_stream, tiles_long; /* two-phase (CSR-stream) tiles, rows longer than a tile */
+  int32_t spmv_grid, spmv_block, spmv_smem_bytes, spmv_stages;
+  int32_t vec_grid, vec_block;
+  int32_t loop_mode;                /* resolved */
+  int32_t sm_count;
+  double last_solve_ms;             /* device time of the last solve (CUDA events around the graph launch) */
+  double last_h2d_ms, last_d2h_ms;  /* host<->device copies of the last host-buffer call */
+  int64_t last_kernel_launches;     /* kernels of this library launched by the last solve / spmv call */
+  int64_t last_iterations;
+  int64_t last_spmv_count;          /* SpMV launches inside the last solve */
+  int64_t device_bytes;             /* device memory held by the handle */
+} b200s_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------ */
+int b200s_version(void);
+int b200s_device_count(void); /* number of CUDA devices with compute capability 10.x (0 = product unusable) */
+int b200s_create(const b200s_config* cfg /* may be NULL: defaults, device = current */, b200s_handle** out);
+void b200s_destroy(b200s_handle* h);
+const char* b200s_last_error(const b200s_handle* h /* NULL: error of the last failed b200s_create */);
+
+/* ---- setup: IterativeSolverBase::analyzePattern / factorize / compute (IterativeSolverBase.h:196-247) ----------
+ * analyze_pattern takes THIS RANK's row block [row_starts[rank], row_starts[rank+1]) of a square `cols` x `cols`
+ * matrix in CSR with GLOBAL column indices (world == 1: the whole matrix, row_starts may be NULL).
+ *   inner_nnz : NULL for a compressed matrix, else Eigen's innerNonZeroPtr (SparseMatrix.h:176-183): row i holds
+ *               entries [rowptr[i], rowptr[i]+inner_nnz[i]).
+ *   uplo      : which stored triangle(s) define the operator.  LOWER / UPPER read one triangle and imply its mirror
+ *               image, as ConjugateGradient<_,Lower> does through selfadjointView (ConjugateGradient.h:202-213); the
+ *               device matrix is then the expanded full CSR.  Only world == 1 supports LOWER / UPPER.
+ * It builds the partition / halo plan, the SpMV tiles with their per-tile row-binning, and uploads the pattern.
+ * factorize uploads the values (same order as the pattern given to analyze_pattern) and builds the
+ * preconditioner: invdiag[j] = 1/A_jj if stored and non-zero else 1 (BasicPreconditioners.h:64-79). */
+int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t nnz, const int32_t* rowptr,
+                          const int32_t* colidx, const int32_t* inner_nnz, int uplo, const int64_t* row_starts);
+int b200s_factorize_f64(b200s_handle* h, const double* values, int precond);
+int b200s_factorize_f32(b200s_handle* h, const float* values, int precond);
+
+/* ---- SpMV: dst = A*x (SparseDenseProduct.h:26-72 + ProductEvaluators.h:348-349) ----------------------------------
+ * Host variant: x has `cols` entries when world == 1, else this rank's `rows` owned entries (the halo is exchanged
+ * on the device); y receives this rank's `rows` entries.
+ * Device variant: same, device pointers; runs `reps` back-to-back products (benchmark path, no PCIe) and returns
+ * the average device time per product in *ms_avg (CUDA events on the library's stream). */
+int b200s_spmv_f64(b200s_handle* h, const double* x, double* y);
+int b200s_spmv_f32(b200s_handle* h, const float* x, float* y);
+int b200s_spmv_device_f64(b200s_handle* h, const double* x_dev, double* y_dev, int reps, float* ms_avg);
+int b200s_spmv_device_f32(b200s_handle* h, const float* x_dev, float* y_dev, int reps, float* ms_avg);
+
+/* ---- solves: Derived::_solve_vector_with_guess_impl (ConjugateGradient.h:197-221, BiCGSTAB.h:193-204) ------------
+ * b, x: this rank's `rows` entries.  use_guess == 0 -> x is zeroed first (IterativeSolverBase.h:399-404), else x
+ * holds the initial guess (solveWithGuess, :316-323).  tol < 0 -> machine epsilon (:413); max_iters < 0 -> 2*cols
+ * (:281-284).  Outputs follow the reference exactly, including: CG counts completed iterations only
+ * (ConjugateGradient.h:77-79,87); ||b|| == 0 gives x = 0 with iters = 0 / error = 0 for CG but iters = max_iters /
+ * error = tol for BiCGSTAB (BiCGSTAB.h:47-51); info = error <= tol ? Success : NoConvergence; NumericalIssue if a
+ * non-finite scalar appeared.  The whole iteration runs on the device (CUDA graph, on-device convergence test);
+ * the host blocks until it is finished. */
+int b200s_cg_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
+                       int64_t* iters_out, double* error_out, int* info_out);
+int b200s_bicgstab_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol,
+                             int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
+int b200s_cg_solve_device_f64(b200s_handle* h, const double* b_dev, double* x_dev, int use_guess, double tol,
+                              int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
+int b200s_bicgstab_solve_device_f64(b200s_handle* h, const double* b_dev, double* x_dev, int use_guess, double tol,
+                                    int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
+
+/* ---- introspection --------------------------------------------------------------------------------------------- */
+int b200s_get_stats(b200s_handle* h, b200s_stats* out /* out->struct_size must be set */);
+/* Copies the preconditioner's inverse diagonal (this rank's rows) to the host: DiagonalPreconditioner::m_invdiag. */
+int b200s_get_invdiag_f64(b200s_handle* h, double* invdiag);
+/* Per-iteration squared residual norms of the last solve (at most `cap`), for trajectory parity;
+ * returns the number written, or a negative status. */
+int64_t b200s_get_residual_history(b200s_handle* h, double* rr, int64_t cap);
+
+/* ---- GPU-free planning, exposed for host-logic tests (no CUDA call is made) ----------------------------------------
+ * Builds the same partition / halo / tile plan analyze_pattern builds and reports it.  `local_colidx` (nnz entries,
+ * optional) receives the remapped column indices: owned column c -> c - row_starts[rank]; ghost g -> rows + g.
+ * `ghost_cols` (capacity ghost_cap, optional) receives the sorted global ids of the ghosts; `send_rows` (capacity
+ * send_cap, optional) the local rows this rank sends, grouped by destination rank; `send_counts` / `recv_counts`
+ * (world entries each, optional) the per-peer counts.  Returns the number of ghosts, or a negative status. */
+int64_t b200s_plan_probe(const b200s_config* cfg, int64_t rows, int64_t cols, int64_t nnz, const int32_t* rowptr,
+                         const int32_t* colidx, const int64_t* row_starts, int32_t* local_colidx,
+                         int64_t* ghost_cols, int64_t ghost_cap, int32_t* send_rows, int64_t send_cap,
+                         int64_t* send_counts, int64_t* recv_counts, b200s_stats* tile_stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPARSE_H */

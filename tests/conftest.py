@@ -1,0 +1,81 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (sm_100) device; run with `-m gpu` on the GPU box")
+
+
+class Golden:
+    """tests/golden/golden_v1.npz: outputs of the unmodified reference (see tests/golden/make_golden.py)."""
+
+    def __init__(self):
+        self.z = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+        self.keys = list(self.z.keys())
+
+    def cases(self, prefix):
+        seen = []
+        for k in self.keys:
+            if k.startswith(prefix + "/") and k.endswith("/matrix"):
+                seen.append(k[: -len("/matrix")])
+        return seen
+
+    def get(self, case, name, default=None):
+        k = f"{case}/{name}"
+        if k in self.z:
+            v = self.z[k]
+            return v.item() if v.ndim == 0 else v
+        return default
+
+    def matrix(self, case):
+        from eigen_git_mirror_b200.workloads import CsrMatrix
+        key = str(self.get(case, "matrix"))
+        g = lambda n: self.z[f"{key}/{n}"]
+        return CsrMatrix(int(g("rows")), int(g("cols")), g("rowptr"), g("colidx"), g("vals"), 0, key)
+
+
+_golden = None
+
+
+@pytest.fixture(scope="session")
+def golden():
+    global _golden
+    if _golden is None:
+        _golden = Golden()
+    return _golden
+
+
+def golden_case_names(prefix):
+    global _golden
+    if _golden is None:
+        _golden = Golden()
+    return _golden.cases(prefix)
+
+
+@pytest.fixture(scope="session")
+def port():
+    from oracle import loader
+    return loader.port()
+
+
+@pytest.fixture(scope="session")
+def variant():
+    """Which ISA variant of the reference build this host reproduces (oracle/loader.host_lanes)."""
+    from oracle import loader
+    return "v4" if loader.host_lanes() == 8 else "v3"
+
+
+@pytest.fixture(scope="session")
+def egm():
+    """The product package, on a machine with a B200.  GPU tests must not silently fall back to anything."""
+    import eigen_git_mirror_b200 as m
+    if m.device_count() < 1:
+        pytest.skip("no sm_100 device visible (GPU tests run under gpurun)")
+    return m

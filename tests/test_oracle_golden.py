@@ -1,0 +1,74 @@
+"""CPU: the plain-C oracle (oracle/oracle.c) is pinned BIT-FOR-BIT to the golden vectors produced by the unmodified
+reference (Eigen compiled from /root/reference, tests/golden/make_golden.py), for the ISA variant of this host."""
+import numpy as np
+import pytest
+
+from conftest import golden_case_names
+
+pytestmark = pytest.mark.timeout(300)
+
+
+@pytest.mark.parametrize("case", golden_case_names("spmv"))
+def test_spmv_bit_exact(case, golden, port, variant):
+    A = golden.matrix(case)
+    x = golden.get(case, "x")
+    y = port.spmv(A, x)  # double: unfused row loop; float: the vectorised-body / fused-epilogue pattern of `variant`
+    assert y.dtype == A.vals.dtype
+    assert np.array_equal(y, golden.get(case, f"y_{variant}"))
+
+
+def test_spmv_float_variants_differ_only_in_rounding(golden):
+    case = "spmv/banded_500_k16/f32"
+    a, b = golden.get(case, "y_v3"), golden.get(case, "y_v4")
+    assert np.max(np.abs(a - b)) < 1e-5 and not np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("case", golden_case_names("symv"))
+def test_selfadjoint_product_bit_exact(case, golden, port):
+    A = golden.matrix(case)
+    y = port.symv(A, golden.get(case, "x"), int(golden.get(case, "uplo")))
+    assert np.array_equal(y, golden.get(case, "y"))
+
+
+def test_jacobi_missing_and_zero_diagonal(golden, port):
+    case = "jacobi/missing_diag_40"
+    A = golden.matrix(case)
+    d = port.jacobi(A)
+    assert d[0] == 1.0 and d[5] == 1.0 and d[39] == 1.0 and d[7] == 1.0  # absent / exactly-zero diagonal -> 1
+    assert np.array_equal(d * golden.get(case, "r"), golden.get(case, "z"))
+
+
+def _run(port, golden, case):
+    A = golden.matrix(case)
+    kind = str(golden.get(case, "kind"))
+    x0 = golden.get(case, "x0") if int(golden.get(case, "has_guess")) else None
+    kw = dict(x0=x0, tol=float(golden.get(case, "tol")), max_iters=int(golden.get(case, "max_iters")),
+              precond=int(golden.get(case, "precond")))
+    if kind == "cg":
+        return port.cg(A, golden.get(case, "b"), uplo=int(golden.get(case, "uplo")), **kw)
+    return port.bicgstab(A, golden.get(case, "b"), **kw)
+
+
+@pytest.mark.parametrize("case", golden_case_names("cg") + golden_case_names("bicgstab"))
+def test_solver_bit_exact(case, golden, port, variant):
+    x, it, err, info = _run(port, golden, case)
+    assert it == int(golden.get(case, f"iters_{variant}"))
+    assert info == int(golden.get(case, f"info_{variant}"))
+    gerr = float(golden.get(case, f"error_{variant}"))
+    assert err == gerr or (np.isnan(err) and np.isnan(gerr))
+    assert np.array_equal(x, golden.get(case, f"x_{variant}"), equal_nan=True)
+
+
+def test_reference_semantics_visible_in_goldens(golden, variant):
+    """The control-flow gotchas of SURVEY.md 8a are present in the reference's own outputs."""
+    g = lambda c, n: golden.get(c, f"{n}_{variant}")
+    # CG, zero rhs: x = 0, iterations 0, error 0 (ConjugateGradient.h:46-52)
+    c = "cg/poisson3d_10/zero_rhs"
+    assert g(c, "iters") == 0 and g(c, "error") == 0 and not g(c, "x").any()
+    # BiCGSTAB, zero rhs: iterations stay maxIterations (2n), error stays the tolerance (BiCGSTAB.h:47-51)
+    c = "bicgstab/convdiff3d_10_g0.5/zero_rhs"
+    assert g(c, "iters") == 2 * 1000 and g(c, "error") == 1e-10 and not g(c, "x").any()
+    # exact guess: no iteration (ConjugateGradient.h:56-61)
+    assert g("cg/poisson3d_10/guess_exact", "iters") == 0
+    # maxIterations = k stops after exactly k iterations with NoConvergence
+    assert g("cg/poisson3d_10/traj_k5", "iters") == 5 and g("cg/poisson3d_10/traj_k5", "info") == 2

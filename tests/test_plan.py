@@ -1,0 +1,68 @@
+"""CPU: host logic of analyze_pattern (csrc/plan.cpp) through the GPU-free b200s_plan_probe."""
+import numpy as np
+import pytest
+
+from eigen_git_mirror_b200 import planning, workloads as wl
+
+
+def test_stencil_tiles_cover_everything():
+    A = wl.poisson3d(20)
+    v = planning.probe(A)
+    st = v.stats
+    assert st["rows"] == A.rows and st["nnz"] == A.nnz and st["ghosts"] == 0
+    assert st["tiles"] >= A.rows // 256
+    # 7-point rows: one thread per row everywhere
+    assert st["tiles_by_lanes"][0] >= st["tiles"] - 1 and st["tiles_stream"] == 0 and st["tiles_long"] == 0
+    assert np.array_equal(v.local_colidx, A.colidx)
+
+
+@pytest.mark.parametrize("k,expect_lg", [(4, 0), (16, 2), (50, 3), (100, 4)])
+def test_lanes_follow_row_length(k, expect_lg):
+    A = wl.banded(4096, k)
+    st = planning.probe(A).stats
+    lanes = st["tiles_by_lanes"]
+    assert int(np.argmax(lanes)) == expect_lg, lanes
+
+
+def test_long_rows_and_stream_tiles():
+    A = wl.powerlaw(3000, 8, max_row=3000)
+    # graft one very long row
+    import scipy.sparse as sp
+    S = A.to_scipy().tolil()
+    S[7, :] = 1.0
+    S = S.tocsr()
+    S.sort_indices()
+    B = wl.CsrMatrix(3000, 3000, S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data)
+    st = planning.probe(B).stats
+    assert st["tiles_long"] == 1
+    assert st["tiles_stream"] > 0
+    assert sum(st["tiles_by_lanes"]) + st["tiles_stream"] + st["tiles_long"] == st["tiles"]
+
+
+def test_tile_caps_are_configurable():
+    A = wl.poisson2d(64)
+    a = planning.probe(A, tile_nnz=512, tile_rows=64).stats
+    b = planning.probe(A, tile_nnz=4096, tile_rows=512).stats
+    assert a["tiles"] > b["tiles"]
+    assert a["tiles"] >= A.rows // 64
+
+
+def test_empty_rows_and_empty_matrix():
+    rowptr = np.array([0, 0, 2, 2, 3], np.int32)
+    A = wl.CsrMatrix(4, 4, rowptr, np.array([0, 3, 2], np.int32), np.array([1.0, 2.0, 3.0]))
+    st = planning.probe(A).stats
+    assert st["rows"] == 4 and st["nnz"] == 3 and st["tiles"] == 1
+    E = wl.CsrMatrix(0, 0, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    assert planning.probe(E).stats["tiles"] == 0
+
+
+def test_invalid_inputs_are_rejected():
+    import eigen_git_mirror_b200 as egm
+    A = wl.poisson2d(8)
+    bad = wl.CsrMatrix(A.rows, A.cols, A.rowptr, A.colidx.copy(), A.vals)
+    bad.colidx[3] = A.cols + 5
+    with pytest.raises(egm.B200Error):
+        planning.probe(bad)
+    rect = wl.CsrMatrix(3, 4, np.array([0, 1, 2, 3], np.int32), np.array([0, 1, 3], np.int32), np.ones(3))
+    with pytest.raises(egm.B200Error):
+        planning.probe(rect)
