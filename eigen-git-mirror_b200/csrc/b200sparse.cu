@@ -686,9 +686,12 @@ int configure_spmv(b200s_handle* h) {
   // stage geometry is decided for the widest scalar (double) so that one plan serves both precisions
   const Plan& p = h->plan;
   size_t stage = spmv_stage_bytes<double>(p.tile_nnz, p.tile_rows_cap);
-  int stages = env_int("B200S_SPMV_STAGES", 4);
+  // Two stages per CTA and as many CTAs per SM as shared memory allows (four with the default 2048-nnz tile):
+  // measured on B200 at 256^3, 4 CTAs x 2 stages reaches 93 % of the copy bandwidth where 2 CTAs x 4 stages
+  // reaches 65 % -- the x gathers need the extra resident warps (profiles/r1_spmv_geometry_sweep.jsonl).
+  int stages = env_int("B200S_SPMV_STAGES", 2);
   stages = std::max(2, std::min(8, stages));
-  size_t budget = 110 * 1024;  // two CTAs per SM out of 227 KB
+  size_t budget = static_cast<size_t>(env_int("B200S_SPMV_SMEM_KB", 56)) * 1024;  // per CTA
   while (stages > 2 && stage * stages > budget) --stages;
   if (stage * stages > 220 * 1024) return fail(h, B200S_ERR_INVALID, "tile_nnz/tile_rows too large for shared memory");
   h->spmv_stages = stages;
@@ -701,7 +704,7 @@ int configure_spmv(b200s_handle* h) {
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_staged_kernel<double, 1>, kSpmvThreads, h->spmv_smem));
   if (occ < 1) return fail(h, B200S_ERR_CUDA, "staged SpMV kernel does not fit on an SM");
-  occ = std::min(occ, env_int("B200S_SPMV_OCC", 2));
+  occ = std::min(occ, env_int("B200S_SPMV_OCC", 8));
   int grid = h->sm_count * occ;
   int ntiles = static_cast<int>(p.tiles.size());
   grid = std::max(1, std::min(grid, std::max(1, ntiles)));

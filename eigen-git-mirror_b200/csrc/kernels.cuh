@@ -313,28 +313,32 @@ __device__ __forceinline__ void tile_rows_reduce(const T* __restrict__ sv, const
     if (r < nrows) {
       int k = srp[r];
       const int k1 = srp[r + 1];
-      if (L == 1) {
-        if (STREAM) {
-          for (; k < k1; ++k) sum = add_rn(sum, sv[k - vb0]);
-        } else {
-          const int kbody = (sizeof(T) == 4 && tail_blk > 0) ? k + ((k1 - k) / tail_blk) * tail_blk : k1;
-          for (; k + 4 <= kbody; k += 4) {
-            const int c0 = sc[k - cb0], c1 = sc[k + 1 - cb0], c2 = sc[k + 2 - cb0], c3 = sc[k + 3 - cb0];
-            const T x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-            sum = add_rn(sum, mul_rn(sv[k - vb0], x0));
-            sum = add_rn(sum, mul_rn(sv[k + 1 - vb0], x1));
-            sum = add_rn(sum, mul_rn(sv[k + 2 - vb0], x2));
-            sum = add_rn(sum, mul_rn(sv[k + 3 - vb0], x3));
-          }
-          for (; k < kbody; ++k) sum = add_rn(sum, mul_rn(sv[k - vb0], __ldg(x + sc[k - cb0])));
-          for (; k < k1; ++k) sum = fma_rn(sv[k - vb0], __ldg(x + sc[k - cb0]), sum);  // float epilogue pattern
-        }
+      if (STREAM) {
+        for (k += lane; k < k1; k += L) sum = add_rn(sum, sv[k - vb0]);
       } else {
-        for (k += lane; k < k1; k += L) {
-          if (STREAM)
-            sum = add_rn(sum, sv[k - vb0]);
-          else
-            sum = add_rn(sum, mul_rn(sv[k - vb0], __ldg(x + sc[k - cb0])));
+        // Batches of B entries per lane with every shared-memory read and every x gather issued before the first
+        // add: one memory latency per batch instead of one per entry.  Slots past the end of the row multiply
+        // 0 * 0 and add +0, which leaves the sum unchanged (the final -0 -> +0 normalisation happens anyway).
+        constexpr int B = (L == 1) ? 8 : 4;
+        const int kfuse = (sizeof(T) == 4 && L == 1 && tail_blk > 0) ? k + ((k1 - k) / tail_blk) * tail_blk : k1;
+        for (k += lane; k < k1; k += B * L) {
+          int c[B];
+          T v[B], xv[B];
+#pragma unroll
+          for (int j = 0; j < B; ++j) {
+            const bool in = (k + j * L) < k1;
+            c[j] = in ? sc[k + j * L - cb0] : 0;
+            v[j] = in ? sv[k + j * L - vb0] : T(0);
+          }
+#pragma unroll
+          for (int j = 0; j < B; ++j) xv[j] = ((k + j * L) < k1) ? __ldg(x + c[j]) : T(0);
+#pragma unroll
+          for (int j = 0; j < B; ++j) {
+            if (sizeof(T) == 4 && L == 1 && (k + j) >= kfuse)
+              sum = fma_rn(v[j], xv[j], sum);  // float: the reference's fused scalar epilogue
+            else
+              sum = add_rn(sum, mul_rn(v[j], xv[j]));
+          }
         }
       }
     }
