@@ -1,0 +1,147 @@
+"""Worker for the multi-process tests (launched once per rank by tests/test_dist_gloo.py and tests/test_gpu_multi.py).
+
+mode "plan" (CPU, gloo): builds the row-block plan through the GPU-free probe, performs the halo exchange the plan
+prescribes with torch.distributed, multiplies the local block with numpy and checks it against the oracle's global
+SpMV -- i.e. partition + ghost numbering + send lists are exactly what a correct distributed product needs.
+
+mode "gpu" (one process per GPU): SpMV, CG and BiCGSTAB through the C ABI on the partitioned problem; rank 0 gathers
+the pieces and compares with the oracle run on the whole problem.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def make(name):
+    from eigen_git_mirror_b200 import workloads as wl
+    if name == "poisson3d":
+        return wl.poisson3d(12), 144
+    if name == "convdiff3d":
+        return wl.convdiff3d(12), 144
+    if name == "varcoef3d":
+        return wl.varcoef3d(10), 1
+    if name == "powerlaw":
+        A = wl.powerlaw(1500, 6, seed=5)
+        # make it diagonally dominant so that CG/BiCGSTAB behave: A <- A + A^T + 40 I
+        S = A.to_scipy()
+        import scipy.sparse as sp
+        S = (S + S.T + 40.0 * sp.identity(A.rows)).tocsr()
+        S.sort_indices()
+        return wl.CsrMatrix(A.rows, A.cols, S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data), 1
+    raise SystemExit(name)
+
+
+def block_of(A, r0, r1):
+    from eigen_git_mirror_b200.workloads import CsrMatrix
+    lo, hi = A.rowptr[r0], A.rowptr[r1]
+    return CsrMatrix(r1 - r0, A.cols, (A.rowptr[r0:r1 + 1] - lo).astype(np.int32), A.colidx[lo:hi].copy(),
+                     A.vals[lo:hi].copy(), r0)
+
+
+def gather_vec(dist, local, starts, group=None):
+    import torch
+    world = dist.get_world_size()
+    n = int(max(np.diff(starts)))
+    buf = torch.zeros(n, dtype=torch.float64)
+    buf[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
+    out = [torch.zeros(n, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    return np.concatenate([out[q].numpy()[: int(starts[q + 1] - starts[q])] for q in range(world)])
+
+
+def main():
+    mode, name = sys.argv[1], sys.argv[2]
+    import torch
+    import torch.distributed as dist
+    import eigen_git_mirror_b200 as egm
+    from eigen_git_mirror_b200 import planning, workloads as wl
+    from oracle import loader
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if mode == "gpu":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group(backend="gloo")
+    A, align = make(name)
+    starts = egm.partition_rows(A.rows, world, align=align)
+    r0, r1 = int(starts[rank]), int(starts[rank + 1])
+    Ab = block_of(A, r0, r1)
+    comm = egm.Communicator.from_torch(starts)
+    port = loader.port()
+    x = wl.random_vector(A.cols, 54321)
+    y_ref = port.spmv(A, x)
+
+    if mode == "plan":
+        v = planning.probe(Ab, comm)
+        # 1. ghosts are exactly the external columns this block references
+        ext = np.unique(Ab.colidx[(Ab.colidx < r0) | (Ab.colidx >= r1)])
+        assert np.array_equal(v.ghosts, ext)
+        # 2. halo exchange as prescribed: I send x[r0 + send_rows], grouped by destination, and receive my ghosts
+        #    ordered by owner = ordered by global column
+        send = x[r0 + v.send_rows]
+        inp = [torch.from_numpy(np.ascontiguousarray(s)) for s in np.split(send, np.cumsum(v.send_counts)[:-1])]
+        # gloo has no all_to_all on every build: emulate with all_gather of padded buffers
+        m = int(max(1, A.rows))
+        pad = torch.zeros(world, m, dtype=torch.float64)
+        for q in range(world):
+            pad[q, : inp[q].shape[0]] = inp[q]
+        gathered = [torch.zeros(world, m, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, pad)
+        ghost_vals = np.concatenate([gathered[q][rank, : int(v.recv_counts[q])].numpy() for q in range(world)])
+        assert np.array_equal(ghost_vals, x[v.ghosts])
+        # 3. local product on [owned | ghost] with the remapped columns equals the oracle's rows
+        x_ext = np.concatenate([x[r0:r1], ghost_vals])
+        Aloc = wl.CsrMatrix(Ab.rows, Ab.rows + len(v.ghosts), Ab.rowptr, v.local_colidx, Ab.vals)
+        assert np.array_equal(port.spmv(Aloc, x_ext), y_ref[r0:r1])
+        assert v.stats["ghosts"] == len(ext) and v.stats["halo_send"] == len(v.send_rows)
+        if name == "poisson3d":  # k-slab partition: one n^2 plane per neighbour, few boundary tiles
+            nb = (rank > 0) + (rank < world - 1)
+            assert len(ext) == 144 * nb and v.stats["tiles_boundary"] <= 2 * nb + 1
+        print(f"rank {rank}: plan ok, ghosts {len(ext)}, send {len(v.send_rows)}")
+    else:
+        # ---- SpMV ----
+        op = egm.SparseOperator(Ab, comm=comm)
+        y = op.multiply(x[r0:r1])
+        assert np.array_equal(y, y_ref[r0:r1]), np.abs(y - y_ref[r0:r1]).max()
+        # ---- solvers ----
+        x_true = wl.random_vector(A.rows, 12345)
+        b = np.asarray(A.to_scipy() @ x_true)
+        if name != "convdiff3d":
+            s = egm.ConjugateGradient(Ab, comm=comm)
+            s.setTolerance(1e-10)
+            xl = s.solve(b[r0:r1])
+            xg = gather_vec(dist, xl, starts)
+            xr, itr, errr, infor = port.cg(A, b, tol=1e-10)
+            rel = np.linalg.norm(xg - xr) / np.linalg.norm(xr)
+            assert s.info() == infor == 0 and abs(s.iterations() - itr) <= max(1, 0.02 * itr), (s.iterations(), itr)
+            assert rel < 1e-8 and s.error() <= 1e-10, rel
+            # warm start + determinism across reruns
+            xl2 = s.solve(b[r0:r1])
+            assert np.array_equal(xl, xl2)
+            xl3 = s.solveWithGuess(b[r0:r1], xl)
+            assert s.iterations() == 0
+            msg = f"cg iters {s.iterations()} rel {rel:.2e}"
+        else:
+            msg = ""
+        s2 = egm.BiCGSTAB(Ab, comm=comm)
+        s2.setTolerance(1e-10)
+        xl = s2.solve(b[r0:r1])
+        xg = gather_vec(dist, xl, starts)
+        xr, itr, errr, infor = port.bicgstab(A, b, tol=1e-10)
+        rel = np.linalg.norm(xg - xr) / np.linalg.norm(xr)
+        assert s2.info() == infor == 0 and abs(s2.iterations() - itr) <= max(2, 0.05 * itr), (s2.iterations(), itr)
+        assert rel < 1e-8 and s2.error() <= 1e-10, rel
+        xl_w = s2.solveWithGuess(b[r0:r1], xl + 1e-6)
+        assert s2.info() == 0
+        print(f"rank {rank}: gpu ok ({name}) {msg}; bicgstab iters {s2.iterations()} rel {rel:.2e}; "
+              f"ghosts {op.stats()['ghosts']}")
+        op.close(); s2.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
