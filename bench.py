@@ -176,6 +176,8 @@ def run_ours(args):
     N = n ** 3
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
         gloo = dist.new_group(backend="gloo")
         starts = egm.partition_rows(N, world, align=n * n)  # k-slabs: one n^2 plane of halo per neighbour

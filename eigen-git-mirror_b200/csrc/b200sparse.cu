@@ -191,9 +191,11 @@ unsigned recv_mask(const b200s_handle* h) {
 }
 
 // ---- kernel launch helpers (all on h->stream; counted) ----
+// `halo_slot` >= 0: x_ext is that extended slot of the peer-visible window and its boundary entries are pushed to the
+// neighbours at the head of the kernel (multi-GPU only).
 template <typename T>
 int launch_spmv(b200s_handle* h, const T* x_ext, T* y, const T* w, int ndot, int epilogue, int gate, bool set_cond,
-                cudaGraphConditionalHandle cond) {
+                cudaGraphConditionalHandle cond, int halo_slot) {
   SpmvArgs<T> a{};
   a.tiles = h->tiles.as<Tile>();
   a.ntiles = static_cast<int>(h->plan.tiles.size());
@@ -211,7 +213,22 @@ int launch_spmv(b200s_handle* h, const T* x_ext, T* y, const T* w, int ndot, int
   a.evict_first = h->evict_first;
   a.recv_mask = recv_mask(h);
   a.history = h->history.as<double>();
+  if (h->plan.world > 1) {
+    if (halo_slot < 0) return fail(h, B200S_ERR_INVALID, "internal: multi-GPU SpMV needs a window slot");
+    if (epilogue == kEpiNone) epilogue = kEpiSpmvOnly;  // the final rendezvous retires the halo sequence number
+    a.halo.enabled = 1;
+    a.halo.send_rows = h->send_rows.as<int32_t>();
+    a.halo.counter = h->halo_counter.as<unsigned>();
+    for (int q = 0; q < h->plan.world; ++q) {
+      a.halo.send_offsets[q] = h->plan.send_offsets[q];
+      a.halo.send_counts[q] = h->plan.send_counts[q];
+      size_t sb = ext_slot_bytes(h->all_rows[q], h->all_ghosts[q]);
+      char* base = static_cast<char*>(h->peer_window[q]) + sb * halo_slot;
+      a.halo.dst[q] = reinterpret_cast<T*>(base) + h->all_rows[q] + h->plan.send_slot0[q];
+    }
+  }
   a.red = make_red(h, epilogue, gate, set_cond, cond);
+  a.red.bump_halo = a.halo.enabled;
   if (h->spmv_impl == B200S_SPMV_DIRECT) {
     const int rows = static_cast<int>(h->plan.rows);
     const int grid = h->sm_count * 8;
@@ -234,29 +251,6 @@ int launch_spmv(b200s_handle* h, const T* x_ext, T* y, const T* w, int ndot, int
     else if (ndot == 1) spmv_staged_kernel<T, 1><<<h->spmv_grid, kSpmvThreads, h->spmv_smem, h->stream>>>(a);
     else spmv_staged_kernel<T, 2><<<h->spmv_grid, kSpmvThreads, h->spmv_smem, h->stream>>>(a);
   }
-  CK(cudaGetLastError());
-  h->last_launches++;
-  return 0;
-}
-
-template <typename T>
-int launch_halo(b200s_handle* h, int slot, int gate) {
-  if (h->plan.world <= 1) return 0;
-  HaloArgs<T> a{};
-  a.x = slot_ptr<T>(h, slot);
-  a.send_rows = h->send_rows.as<int32_t>();
-  for (int q = 0; q < h->plan.world; ++q) {
-    a.send_offsets[q] = h->plan.send_offsets[q];
-    a.send_counts[q] = h->plan.send_counts[q];
-    size_t sb = ext_slot_bytes(h->all_rows[q], h->all_ghosts[q]);
-    char* base = static_cast<char*>(h->peer_window[q]) + sb * slot;
-    a.dst[q] = reinterpret_cast<T*>(base) + h->all_rows[q] + h->plan.send_slot0[q];
-  }
-  a.counter = h->halo_counter.as<unsigned>();
-  a.red = make_red(h, kEpiNone, gate, false, 0);
-  int64_t n = static_cast<int64_t>(h->plan.send_rows.size());
-  int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (n + kVecThreads - 1) / kVecThreads)));
-  halo_push_kernel<T><<<grid, kVecThreads, 0, h->stream>>>(a);
   CK(cudaGetLastError());
   h->last_launches++;
   return 0;
@@ -291,9 +285,8 @@ VecArgs make_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGra
 // ---- the iteration bodies (enqueued either under stream capture or directly) ----
 int enqueue_cg_init(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
   int rc;
-  if ((rc = launch_halo<double>(h, kSlotX, kGateGuess))) return rc;
   if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotX), h->q.as<double>(), nullptr, 0, kEpiNone, kGateGuess,
-                                false, 0)))
+                                false, 0, kSlotX)))
     return rc;
   VecArgs a = make_vec(h, kEpiCgInit, kGateNone, set_cond, cond);
   LAUNCH_VEC(cg_init_kernel, a);
@@ -302,9 +295,8 @@ int enqueue_cg_init(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle c
 
 int enqueue_cg_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
   int rc;
-  if ((rc = launch_halo<double>(h, kSlotP, kGateLoop))) return rc;
   if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotP), h->q.as<double>(), nullptr, 1, kEpiCgPAp, kGateLoop,
-                                false, 0)))
+                                false, 0, kSlotP)))
     return rc;
   VecArgs u = make_vec(h, kEpiCgUpdate, kGateLoop, set_cond, cond);
   LAUNCH_VEC(cg_update_kernel, u);
@@ -323,9 +315,8 @@ VecArgs make_bicg_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cu
 
 int enqueue_bicg_init(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
   int rc;
-  if ((rc = launch_halo<double>(h, kSlotX, kGateGuess))) return rc;
   if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotX), h->t.as<double>(), nullptr, 0, kEpiNone, kGateGuess,
-                                false, 0)))
+                                false, 0, kSlotX)))
     return rc;
   VecArgs a = make_bicg_vec(h, kEpiBiInit, kGateNone, set_cond, cond);
   LAUNCH_VEC(bicg_init_kernel, a);
@@ -335,23 +326,20 @@ int enqueue_bicg_init(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle
 int enqueue_bicg_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
   int rc;
   // re-orthogonalisation branch (BiCGSTAB.h:72-81), live only when the control state asks for it
-  if ((rc = launch_halo<double>(h, kSlotX, kGateRestart))) return rc;
   if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotX), h->t.as<double>(), nullptr, 0, kEpiNone,
-                                kGateRestart, false, 0)))
+                                kGateRestart, false, 0, kSlotX)))
     return rc;
   VecArgs rs = make_bicg_vec(h, kEpiBiRestart, kGateRestart, false, 0);
   LAUNCH_VEC(bicg_restart_kernel, rs);
   VecArgs pa = make_bicg_vec(h, kEpiNone, kGateLoop, false, 0);
   LAUNCH_VEC(bicg_p_kernel, pa);
-  if ((rc = launch_halo<double>(h, kSlotP, kGateLoop))) return rc;
   if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotP), h->q.as<double>(), h->r0.as<double>(), 1, kEpiBiR0V,
-                                kGateLoop, false, 0)))
+                                kGateLoop, false, 0, kSlotP)))
     return rc;
   VecArgs sa = make_bicg_vec(h, kEpiNone, kGateLoop, false, 0);
   LAUNCH_VEC(bicg_s_kernel, sa);
-  if ((rc = launch_halo<double>(h, kSlotZ, kGateLoop))) return rc;
   if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotZ), h->t.as<double>(), h->s.as<double>(), 2, kEpiBiTsTt,
-                                kGateLoop, false, 0)))
+                                kGateLoop, false, 0, kSlotZ)))
     return rc;
   VecArgs ua = make_bicg_vec(h, kEpiBiUpdate, kGateLoop, set_cond, cond);
   LAUNCH_VEC(bicg_update_kernel, ua);
@@ -598,19 +586,17 @@ int spmv_device_impl(b200s_handle* h, const T* x_dev, T* y_dev, int reps, float*
   if (reps < 1) reps = 1;
   const T* x_ext = x_dev;
   h->last_launches = 0;
+  if (h->plan.world > 1) {  // the product reads x from the peer-visible window: [owned | ghost]
+    T* xs = slot_ptr<T>(h, kSlotSpmv);
+    if (x_dev != xs) CK(cudaMemcpyAsync(xs, x_dev, static_cast<size_t>(h->plan.rows) * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    x_ext = xs;
+  }
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < reps; ++i) {
     int rc;
-    if (h->plan.world > 1) {
-      T* xs = slot_ptr<T>(h, kSlotSpmv);
-      if (x_dev != xs) CK(cudaMemcpyAsync(xs, x_dev, static_cast<size_t>(h->plan.rows) * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
-      if ((rc = launch_halo<T>(h, kSlotSpmv, kGateNone))) return rc;
-      x_ext = xs;
-      // a cross-rank rendezvous after each product keeps single-buffered ghost slots safe for the next push
-      if ((rc = launch_spmv<T>(h, x_ext, y_dev, nullptr, 0, kEpiSpmvOnly, kGateNone, false, 0))) return rc;
-    } else {
-      if ((rc = launch_spmv<T>(h, x_ext, y_dev, nullptr, 0, kEpiNone, kGateNone, false, 0))) return rc;
-    }
+    // multi-GPU: each launch pushes the halo, multiplies, and ends in a cross-rank rendezvous (kEpiSpmvOnly) that
+    // keeps the single-buffered ghost slots safe for the next push
+    if ((rc = launch_spmv<T>(h, x_ext, y_dev, nullptr, 0, kEpiNone, kGateNone, false, 0, kSlotSpmv))) return rc;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));

@@ -88,6 +88,7 @@ struct RedCtx {
   int gate;
   unsigned long long cond_handle;  // cudaGraphConditionalHandle or 0
   int set_cond;                    // last block updates the WHILE condition after the epilogue
+  int bump_halo;                   // the kernel carried a halo exchange (multi-GPU SpMV)
   CommDev comm;
 };
 

@@ -6,7 +6,8 @@
 //   spmv_direct_kernel   plain sub-warp-per-row CSR SpMV from global memory (A/B baseline for the ncu evidence).
 //   cg_* / bicg_*        the vector updates of ConjugateGradient.h:63-87 and BiCGSTAB.h:82-102, each fused with
 //                        the dot products that follow it.
-//   halo_push_kernel     boundary entries of a vector stored into the neighbours' ghost slots over NVLink.
+//   (halo push)          fused into the head of the SpMV kernels: boundary entries of x are stored into the
+//                        neighbours' ghost slots over NVLink while the interior tiles are already streaming.
 //
 // Reductions are deterministic: every thread accumulates a fixed set of elements in a fixed order, warps are
 // folded with shuffles, warps of a CTA in a fixed tree, CTAs by the last-arriving CTA in index order, ranks in
@@ -264,9 +265,59 @@ __device__ __forceinline__ void finish_reduction(const RedCtx& ctx, double (&v)[
 #pragma unroll
     for (int j = 0; j < NV; ++j) r[j] = t[j];
     allreduce_ranks(ctx.comm, ctx.S, r, NV);
+    if (ctx.bump_halo) ctx.S->halo_seq++;  // this kernel carried a halo exchange: retire its sequence number
     run_epilogue(ctx, r, history);
     if (ctx.set_cond) cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(ctx.cond_handle), ctx.S->stop ? 0u : 1u);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------- halo push
+// Send plan of one rank: which owned entries go to which peer's ghost slots (pointers are NVLink-mapped peer memory).
+template <typename T>
+struct HaloArgs {
+  int enabled;                // world > 1
+  const int32_t* send_rows;   // local rows to send, grouped by destination
+  long long send_offsets[kMaxWorld];
+  long long send_counts[kMaxWorld];
+  T* dst[kMaxWorld];          // peer q's ghost slots for my entries
+  unsigned int* counter;      // CTA ticket for "all my stores are out"
+};
+
+// Every CTA stores its share of the boundary entries straight into the peers' ghost slots, fences, and takes a
+// ticket; the last CTA publishes the new halo sequence number to the peers.  The sequence number is S->halo_seq + 1,
+// where S->halo_seq is only advanced by the kernel's final single-thread epilogue, i.e. it is stable while any CTA of
+// this kernel (pusher or waiter) reads it.
+template <typename T>
+__device__ __forceinline__ void halo_push(const HaloArgs<T>& hl, const CommDev& c, const Scalars* S, const T* x) {
+  for (int q = 0; q < c.world; ++q) {
+    const long long n = hl.send_counts[q];
+    if (n == 0) continue;
+    const int32_t* rows = hl.send_rows + hl.send_offsets[q];
+    T* dst = hl.dst[q];
+    for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < n;
+         k += static_cast<long long>(gridDim.x) * blockDim.x)
+      dst[k] = x[rows[k]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(hl.counter, 1u);
+    if (ticket == gridDim.x - 1) {
+      *hl.counter = 0;
+      __threadfence_system();
+      const unsigned seq = S->halo_seq + 1;
+      for (int q = 0; q < c.world; ++q)
+        if (hl.send_counts[q] > 0) st_release_sys(c.halo_flag_peer[q] + c.rank, seq);
+    }
+  }
+}
+
+__device__ __forceinline__ void halo_wait(const CommDev& c, const Scalars* S, unsigned recv_mask) {
+  const unsigned want = S->halo_seq + 1;
+  for (int src = 0; src < c.world; ++src)
+    if (recv_mask & (1u << src))
+      while (static_cast<int>(ld_acquire_sys(c.halo_flag_self + src) - want) < 0) {
+      }
 }
 
 // ------------------------------------------------------------------------------------------- staged CSR SpMV
@@ -285,6 +336,7 @@ struct SpmvArgs {
   int tail_blk;     // float only: reference rounding pattern (0 = every product rounded)
   int evict_first;  // stream the matrix through L2 with an evict-first policy
   unsigned recv_mask;  // ranks whose halo must have arrived before boundary tiles (multi-GPU)
+  HaloArgs<T> halo;    // this rank's pushes, issued at the head of the kernel
   double* history;
   RedCtx red;
 };
@@ -409,6 +461,8 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
       const int t = blockIdx.x + s * G;
       if (t < a.ntiles) issue(t, s);
     }
+  // multi-GPU: my boundary entries go out to the neighbours while the first tiles are in flight
+  if (a.halo.enabled) halo_push<T>(a.halo, a.red.comm, a.red.S, a.x);
 
   double d0 = 0.0, d1 = 0.0;
   const T* w = (NDOT >= 1) ? (a.w ? a.w : a.x) : nullptr;
@@ -425,13 +479,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
     const int lg = (tl.meta >> 16) & 0xFF;
 
     if (!halo_ready && t >= a.first_boundary_tile) {  // ghost entries must have landed (multi-GPU)
-      if (tid == 0) {
-        const unsigned want = a.red.S->halo_seq;
-        for (int src = 0; src < a.red.comm.world; ++src)
-          if (a.recv_mask & (1u << src))
-            while (static_cast<int>(ld_acquire_sys(a.red.comm.halo_flag_self + src) - want) < 0) {
-            }
-      }
+      if (tid == 0) halo_wait(a.red.comm, a.red.S, a.recv_mask);
       __syncthreads();
       halo_ready = true;
     }
@@ -525,14 +573,9 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_direct_kernel(const SpmvArg
   const long long ngrp = (static_cast<long long>(gridDim.x) * kSpmvThreads) >> LG;
   const T* w = (NDOT >= 1) ? (a.w ? a.w : a.x) : nullptr;
   double d0 = 0.0, d1 = 0.0;
+  if (a.halo.enabled) halo_push<T>(a.halo, a.red.comm, a.red.S, a.x);
   if (a.recv_mask != 0) {  // direct kernel has no interior/boundary split: wait for the halo up front
-    if (threadIdx.x == 0) {
-      const unsigned want = a.red.S->halo_seq;
-      for (int src = 0; src < a.red.comm.world; ++src)
-        if (a.recv_mask & (1u << src))
-          while (static_cast<int>(ld_acquire_sys(a.red.comm.halo_flag_self + src) - want) < 0) {
-          }
-    }
+    if (threadIdx.x == 0) halo_wait(a.red.comm, a.red.S, a.recv_mask);
     __syncthreads();
   }
   for (long long base = 0; base < rows; base += ngrp) {
@@ -809,47 +852,6 @@ __global__ void __launch_bounds__(kVecThreads) finalize_kernel(const VecArgs a) 
 // Sets the WHILE condition from the control state (used after the init phase and by chunk boundaries).
 __global__ void set_condition_kernel(const Scalars* S, unsigned long long handle) {
   cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(handle), S->stop ? 0u : 1u);
-}
-
-// ---------------------------------------------------------------------------------------------------- halo push
-template <typename T>
-struct HaloArgs {
-  const T* x;                 // owned entries of the vector being exchanged
-  const int32_t* send_rows;   // grouped by destination
-  long long send_offsets[kMaxWorld];
-  long long send_counts[kMaxWorld];
-  T* dst[kMaxWorld];          // peer's ghost slots for my entries (NVLink-mapped)
-  unsigned int* counter;
-  RedCtx red;                 // S, gate, comm
-};
-
-template <typename T>
-__global__ void __launch_bounds__(kVecThreads) halo_push_kernel(const HaloArgs<T> a) {
-  __shared__ int s_last;
-  if (gated_out(a.red.S, a.red.gate)) return;
-  const CommDev& c = a.red.comm;
-  for (int q = 0; q < c.world; ++q) {
-    const long long n = a.send_counts[q];
-    const int32_t* rows = a.send_rows + a.send_offsets[q];
-    T* dst = a.dst[q];
-    for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < n;
-         k += static_cast<long long>(gridDim.x) * blockDim.x)
-      dst[k] = a.x[rows[k]];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(a.counter, 1u);
-    s_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    *a.counter = 0;
-    __threadfence_system();
-    const unsigned seq = ++a.red.S->halo_seq;
-    for (int q = 0; q < c.world; ++q)
-      if (a.send_counts[q] > 0) st_release_sys(c.halo_flag_peer[q] + c.rank, seq);
-  }
 }
 
 }  // namespace b200s
