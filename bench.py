@@ -240,6 +240,9 @@ def run_ours(args):
     iters = s.iterations()
     err, info = s.error(), s.info()
     value = iters_total / (dev_ms * 1e-3)
+    timeline = s.timeline()
+    if os.environ.get("B200S_BENCH_TIMELINES"):
+        print(f"[rank {rank}] timeline {json.dumps(timeline)}", file=sys.stderr)
 
     # ---- end-to-end arm through the host API: pinned host b -> device, solve, x -> pinned host ----
     xh = x_pin.numpy()
@@ -328,6 +331,7 @@ def run_ours(args):
             "spmv": {"gbs": achieved, "frac_of_hbm": achieved / (peak * world), "ms": spmv_ms},
             "iteration": {"bytes": it_bytes, "gbs": it_gbs, "frac_of_hbm": it_gbs / (peak * world),
                           "us_per_iteration": 1e3 * dev_ms / max(1, iters_total)},
+            "timeline_rank0": timeline,
             "clocks": clocks,
             "cpu_baseline": cpu_baseline,
         }

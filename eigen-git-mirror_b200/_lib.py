@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         getattr(L, name).argtypes = solve_args
     L.b200s_get_stats.argtypes = [H, C.POINTER(Stats)]
     L.b200s_get_invdiag_f64.argtypes = [H, vp]
+    L.b200s_get_timeline.argtypes = [H, vp, C.c_int]
     L.b200s_get_residual_history.argtypes = [H, vp, i64]
     L.b200s_get_residual_history.restype = i64
     L.b200s_plan_probe.argtypes = [C.POINTER(Config), i64, i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp,

@@ -217,6 +217,11 @@ int launch_spmv(b200s_handle* h, const T* x_ext, T* y, const T* w, int ndot, int
     if (halo_slot < 0) return fail(h, B200S_ERR_INVALID, "internal: multi-GPU SpMV needs a window slot");
     if (epilogue == kEpiNone) epilogue = kEpiSpmvOnly;  // the final rendezvous retires the halo sequence number
     a.halo.enabled = 1;
+    {
+      const int grid = (h->spmv_impl == B200S_SPMV_DIRECT) ? h->sm_count * 8 : h->spmv_grid;
+      const int64_t total = static_cast<int64_t>(h->plan.send_rows.size());
+      a.halo.npush = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(grid, (total + 2047) / 2048)));
+    }
     a.halo.send_rows = h->send_rows.as<int32_t>();
     a.halo.counter = h->halo_counter.as<unsigned>();
     for (int q = 0; q < h->plan.world; ++q) {
@@ -949,6 +954,18 @@ int b200s_get_invdiag_f64(b200s_handle* h, double* invdiag) {
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(invdiag, h->invdiag.p, static_cast<size_t>(h->plan.rows) * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return B200S_OK;
+}
+
+int b200s_get_timeline(b200s_handle* h, double* out, int cap) {
+  // out[0..11] = microseconds per epilogue kind (kernel + launch gap up to that reduction), out[12..23] = counts,
+  // out[24] = all-reduce us, out[25] = halo wait us (CTA 0), out[26] = first->last epilogue us
+  if (!h || !out || cap < 27 || !h->hS) return B200S_ERR_INVALID;
+  const Scalars& S = *h->hS;
+  for (int i = 0; i < 12; ++i) { out[i] = S.t_phase[i] * 1e-3; out[12 + i] = static_cast<double>(S.n_phase[i]); }
+  out[24] = S.t_allreduce * 1e-3;
+  out[25] = S.t_halo_wait * 1e-3;
+  out[26] = (S.t_end - S.t_first) * 1e-3;
   return B200S_OK;
 }
 

@@ -41,6 +41,13 @@ struct Scalars {
   long long hist_len;
   unsigned int red_seq;   // cross-rank reduction sequence number (multi-GPU mailboxes)
   unsigned int halo_seq;  // halo-exchange sequence number
+  // device-side timeline (globaltimer ns), accumulated per solve: where an iteration's time goes
+  unsigned long long t_last;          // time of the previous reduction epilogue
+  unsigned long long t_phase[12];     // [epilogue kind] time since the previous epilogue (kernel + launch gap)
+  unsigned long long n_phase[12];
+  unsigned long long t_allreduce;     // spent inside the cross-rank all-reduce (stores, fence, waiting for peers)
+  unsigned long long t_halo_wait;     // spent by CTA 0 waiting for ghost entries
+  unsigned long long t_first, t_end;
 };
 
 // What the last block of a reduction does with the reduced values.

@@ -68,6 +68,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -128,6 +133,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double* scratch /*
 __device__ __forceinline__ void allreduce_ranks(const CommDev& c, Scalars* S, double* v, int n) {
   const unsigned seq = ++S->red_seq;
   if (c.world <= 1) return;
+  const unsigned long long t0 = globaltimer_ns();
   const int par = seq & 1;
   for (int q = 0; q < c.world; ++q) {
     double* box = ((q == c.rank) ? c.box_self : c.box_peer[q]) + (par * kMaxWorld + c.rank) * 4;
@@ -146,6 +152,7 @@ __device__ __forceinline__ void allreduce_ranks(const CommDev& c, Scalars* S, do
     const double* box = c.box_self + (par * kMaxWorld + src) * 4;
     for (int j = 0; j < n; ++j) v[j] += ld_relaxed_sys_f64(box + j);
   }
+  S->t_allreduce += globaltimer_ns() - t0;
 }
 
 // --------------------------------------------------------------------------------- scalar logic of the solvers
@@ -266,6 +273,22 @@ __device__ __forceinline__ void finish_reduction(const RedCtx& ctx, double (&v)[
     for (int j = 0; j < NV; ++j) r[j] = t[j];
     allreduce_ranks(ctx.comm, ctx.S, r, NV);
     if (ctx.bump_halo) ctx.S->halo_seq++;  // this kernel carried a halo exchange: retire its sequence number
+    {
+      Scalars* S = ctx.S;
+      const unsigned long long now = globaltimer_ns();
+      const int e = ctx.epilogue;
+      if (e == kEpiCgInit || e == kEpiBiInit) {
+        for (int i = 0; i < 12; ++i) { S->t_phase[i] = 0; S->n_phase[i] = 0; }
+        S->t_first = now;
+        S->t_allreduce = 0;
+        S->t_halo_wait = 0;
+      } else if (e > 0 && e < 12) {
+        S->t_phase[e] += now - S->t_last;
+        S->n_phase[e]++;
+      }
+      S->t_last = now;
+      S->t_end = now;
+    }
     run_epilogue(ctx, r, history);
     if (ctx.set_cond) cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(ctx.cond_handle), ctx.S->stop ? 0u : 1u);
   }
@@ -276,6 +299,7 @@ __device__ __forceinline__ void finish_reduction(const RedCtx& ctx, double (&v)[
 template <typename T>
 struct HaloArgs {
   int enabled;                // world > 1
+  int npush;                  // CTAs [0, npush) carry the push; the others go straight to their tiles
   const int32_t* send_rows;   // local rows to send, grouped by destination
   long long send_offsets[kMaxWorld];
   long long send_counts[kMaxWorld];
@@ -289,20 +313,21 @@ struct HaloArgs {
 // this kernel (pusher or waiter) reads it.
 template <typename T>
 __device__ __forceinline__ void halo_push(const HaloArgs<T>& hl, const CommDev& c, const Scalars* S, const T* x) {
+  if (static_cast<int>(blockIdx.x) >= hl.npush) return;
   for (int q = 0; q < c.world; ++q) {
     const long long n = hl.send_counts[q];
     if (n == 0) continue;
     const int32_t* rows = hl.send_rows + hl.send_offsets[q];
     T* dst = hl.dst[q];
     for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < n;
-         k += static_cast<long long>(gridDim.x) * blockDim.x)
+         k += static_cast<long long>(hl.npush) * blockDim.x)
       dst[k] = x[rows[k]];
   }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned ticket = atomicAdd(hl.counter, 1u);
-    if (ticket == gridDim.x - 1) {
+    if (ticket == static_cast<unsigned>(hl.npush) - 1) {
       *hl.counter = 0;
       __threadfence_system();
       const unsigned seq = S->halo_seq + 1;
@@ -479,7 +504,11 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
     const int lg = (tl.meta >> 16) & 0xFF;
 
     if (!halo_ready && t >= a.first_boundary_tile) {  // ghost entries must have landed (multi-GPU)
-      if (tid == 0) halo_wait(a.red.comm, a.red.S, a.recv_mask);
+      if (tid == 0) {
+        const unsigned long long t0 = (blockIdx.x == 0) ? globaltimer_ns() : 0ull;
+        halo_wait(a.red.comm, a.red.S, a.recv_mask);
+        if (blockIdx.x == 0) a.red.S->t_halo_wait += globaltimer_ns() - t0;
+      }
       __syncthreads();
       halo_ready = true;
     }

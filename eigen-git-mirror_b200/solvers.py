@@ -337,6 +337,17 @@ class _IterativeSolverBase(SparseOperator):
         self._iterations, self._error, self._info = it.value, err.value, info.value
         return x_dev
 
+    def timeline(self) -> dict:
+        """Device-side timeline of the last solve on this rank (see b200s_get_timeline)."""
+        out = np.zeros(27)
+        self._hd.check(self._hd.L.b200s_get_timeline(self._hd.h, _ptr(out), 27))
+        names = {1: "spmv_only", 2: "cg_init", 3: "spmv_pAp", 4: "cg_update", 5: "bicg_init", 6: "spmv_r0v",
+                 7: "spmv_ts_tt", 8: "bicg_update", 9: "bicg_restart"}
+        d = {f"{names[e]}_us_avg": out[e] / out[12 + e] for e in names if out[12 + e] > 0}
+        d.update(allreduce_us_total=out[24], halo_wait_us_total=out[25], span_us=out[26],
+                 reductions=int(out[12:24].sum()))
+        return d
+
     def residual_history(self, cap: int = 1 << 16) -> np.ndarray:
         rr = np.empty(cap, dtype=np.float64)
         n = self._hd.L.b200s_get_residual_history(self._hd.h, _ptr(rr), cap)

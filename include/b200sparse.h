@@ -152,6 +152,12 @@ int b200s_get_invdiag_f64(b200s_handle* h, double* invdiag);
  * returns the number written, or a negative status. */
 int64_t b200s_get_residual_history(b200s_handle* h, double* rr, int64_t cap);
 
+/* Device-side timeline of the last solve (globaltimer, this rank): out[e] / out[12+e] = microseconds / count of the
+ * interval ending at reduction kind e (1 spmv-only, 2 cg-init, 3 p.Ap, 4 cg-update, 5 bicg-init, 6 r0.v, 7 t.s/t.t,
+ * 8 bicg-update, 9 restart), each including the launch gap before it; out[24] = time inside cross-rank all-reduces,
+ * out[25] = time CTA 0 waited for halo entries, out[26] = first-to-last reduction.  cap >= 27. */
+int b200s_get_timeline(b200s_handle* h, double* out, int cap);
+
 /* ---- GPU-free planning, exposed for host-logic tests (no CUDA call is made) ----------------------------------------
  * Builds the same partition / halo / tile plan analyze_pattern builds and reports it.  `local_colidx` (nnz entries,
  * optional) receives the remapped column indices: owned column c -> c - row_starts[rank]; ghost g -> rows + g.
