@@ -161,7 +161,7 @@ CommDev make_comm(const b200s_handle* h) {
     size_t sb = ext_slot_bytes(h->all_rows[q], h->all_ghosts[q]);
     char* base = static_cast<char*>(h->peer_window[q]);
     size_t box_off = sb * kNumSlots;
-    size_t flag_off = box_off + sizeof(double) * 2 * kMaxWorld * 4;
+    size_t flag_off = box_off + sizeof(unsigned long long) * 2 * kMaxWorld * kBoxWords;
     size_t halo_off = flag_off + sizeof(unsigned) * 2 * kMaxWorld;
     c.box_peer[q] = reinterpret_cast<double*>(base + box_off);
     c.flag_peer[q] = reinterpret_cast<unsigned*>(base + flag_off);
@@ -854,7 +854,7 @@ int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t n
   }
   h->slot_bytes = ext_slot_bytes(p.rows, mine[1]);
   h->box_off = h->slot_bytes * kNumSlots;
-  h->flag_off = h->box_off + sizeof(double) * 2 * kMaxWorld * 4;
+  h->flag_off = h->box_off + sizeof(unsigned long long) * 2 * kMaxWorld * kBoxWords;
   h->halo_flag_off = h->flag_off + sizeof(unsigned) * 2 * kMaxWorld;
   h->window_bytes = h->halo_flag_off + sizeof(unsigned) * kMaxWorld + 256;
   for (int q = 0; q < static_cast<int>(h->peer_window.size()); ++q)
