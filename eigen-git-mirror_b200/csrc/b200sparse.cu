@@ -64,7 +64,8 @@ struct b200s_handle {
   std::vector<void*> peer_window;  // [world], IPC-mapped (self: window.p)
   std::vector<int64_t> all_rows, all_ghosts;
   DevBuf b, r, q, r0, s, t, yout;
-  DevBuf scalars, partials, counter, halo_counter, history;
+  DevBuf scalars, partials, counter, halo_counter, history, gridbar;
+  int persist_grid = 0;
   Scalars* hS = nullptr;  // pinned mirror
   // launch geometry
   int spmv_grid = 0, spmv_stages = 0, spmv_smem = 0, vec_grid = 0;
@@ -194,9 +195,23 @@ unsigned recv_mask(const b200s_handle* h) {
 // `halo_slot` >= 0: x_ext is that extended slot of the peer-visible window and its boundary entries are pushed to the
 // neighbours at the head of the kernel (multi-GPU only).
 template <typename T>
+int make_spmv_args(b200s_handle* h, SpmvArgs<T>& a, const T* x_ext, T* y, const T* w, int epilogue, int gate,
+                   bool set_cond, cudaGraphConditionalHandle cond, int halo_slot);
+template <typename T>
+int launch_spmv_args(b200s_handle* h, const SpmvArgs<T>& a, int ndot);
+
+template <typename T>
 int launch_spmv(b200s_handle* h, const T* x_ext, T* y, const T* w, int ndot, int epilogue, int gate, bool set_cond,
                 cudaGraphConditionalHandle cond, int halo_slot) {
   SpmvArgs<T> a{};
+  int rc0 = make_spmv_args<T>(h, a, x_ext, y, w, epilogue, gate, set_cond, cond, halo_slot);
+  if (rc0) return rc0;
+  return launch_spmv_args<T>(h, a, ndot);
+}
+
+template <typename T>
+int make_spmv_args(b200s_handle* h, SpmvArgs<T>& a, const T* x_ext, T* y, const T* w, int epilogue, int gate,
+                   bool set_cond, cudaGraphConditionalHandle cond, int halo_slot) {
   a.tiles = h->tiles.as<Tile>();
   a.ntiles = static_cast<int>(h->plan.tiles.size());
   a.first_boundary_tile = a.ntiles - h->plan.n_boundary_tiles;
@@ -234,6 +249,11 @@ int launch_spmv(b200s_handle* h, const T* x_ext, T* y, const T* w, int ndot, int
   }
   a.red = make_red(h, epilogue, gate, set_cond, cond);
   a.red.bump_halo = a.halo.enabled;
+  return 0;
+}
+
+template <typename T>
+int launch_spmv_args(b200s_handle* h, const SpmvArgs<T>& a, int ndot) {
   if (h->spmv_impl == B200S_SPMV_DIRECT) {
     const int rows = static_cast<int>(h->plan.rows);
     const int grid = h->sm_count * 8;
@@ -310,6 +330,23 @@ int enqueue_cg_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle c
   return 0;
 }
 
+// The whole CG loop as one cooperative kernel (B200S_LOOP_PERSISTENT).
+int launch_cg_persistent(b200s_handle* h) {
+  CgPersistArgs a{};
+  int rc = make_spmv_args<double>(h, a.sp, slot_ptr<double>(h, kSlotP), h->q.as<double>(), nullptr, kEpiCgPAp,
+                                  kGateNone, false, 0, kSlotP);
+  if (rc) return rc;
+  if (a.sp.halo.enabled) a.sp.halo.npush = std::min(a.sp.halo.npush, h->persist_grid);
+  a.ve = make_vec(h, kEpiCgUpdate, kGateNone, false, 0);
+  a.bar_count = h->gridbar.as<unsigned>();
+  a.bar_gen = h->gridbar.as<unsigned>() + 32;
+  void* params[] = {&a};
+  CK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(h->persist_grid), dim3(kSpmvThreads), params,
+                                 static_cast<size_t>(h->spmv_smem), h->stream));
+  h->last_launches++;
+  return 0;
+}
+
 // BiCGSTAB vector roles: x = slot X (ext), y = slot P (ext), z = slot Z (ext), p = h->yout, v = h->q, t = h->t
 VecArgs make_bicg_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGraphConditionalHandle cond) {
   VecArgs a = make_vec(h, epilogue, gate, set_cond, cond);
@@ -363,7 +400,7 @@ typedef int (*enqueue_fn)(b200s_handle*, bool, cudaGraphConditionalHandle);
 int build_graphs(b200s_handle* h, GraphSet& g, enqueue_fn init, enqueue_fn body) {
   if (g.built) return 0;
   int64_t saved = h->last_launches;
-  if (h->loop_mode == B200S_LOOP_WHILE_GRAPH) {
+  if (h->loop_mode == B200S_LOOP_WHILE_GRAPH || h->loop_mode == B200S_LOOP_PERSISTENT) {
     CK(cudaGraphCreate(&g.graph, 0));
     cudaGraphConditionalHandle cond;
     CK(cudaGraphConditionalHandleCreate(&cond, g.graph, 0, cudaGraphCondAssignDefault));
@@ -473,7 +510,13 @@ int run_solve(b200s_handle* h, bool bicg, const double* b_dev, double* x_dev, in
 
   h->last_launches = 0;
   CK(cudaEventRecord(h->ev0, h->stream));
-  if (h->loop_mode == B200S_LOOP_WHILE_GRAPH) {
+  const bool persistent = (h->loop_mode == B200S_LOOP_PERSISTENT) && !bicg && h->spmv_impl != B200S_SPMV_DIRECT;
+  const bool while_graph = (h->loop_mode == B200S_LOOP_WHILE_GRAPH) || (h->loop_mode == B200S_LOOP_PERSISTENT && !persistent);
+  if (persistent) {
+    if ((rc = enqueue_cg_init(h, false, 0))) return rc;
+    if ((rc = launch_cg_persistent(h))) return rc;
+    if ((rc = enqueue_finalize(h))) return rc;
+  } else if (while_graph) {
     CK(cudaGraphLaunch(g.exec, h->stream));
   } else {
     if (h->loop_mode == B200S_LOOP_CHUNKED_GRAPH) {
@@ -523,7 +566,7 @@ int run_solve(b200s_handle* h, bool bicg, const double* b_dev, double* x_dev, in
   if (info_out) *info_out = info;
   h->last_iterations = iters;
   h->last_spmv = S.spmv_count;
-  if (h->loop_mode == B200S_LOOP_WHILE_GRAPH) {
+  if (while_graph) {
     // body executions: one per SpMV launched inside the loop (CG: 1 per pass; BiCGSTAB: 2 per pass + restarts)
     int64_t init_spmv = use_guess ? 1 : 0;
     if (bicg) init_spmv = 1;  // counted by kEpiBiInit regardless (the gated launch still happens)
@@ -700,6 +743,13 @@ int configure_spmv(b200s_handle* h) {
   int ntiles = static_cast<int>(p.tiles.size());
   grid = std::max(1, std::min(grid, std::max(1, ntiles)));
   h->spmv_grid = std::min(grid, kMaxGrid);
+  {
+    CK(cudaFuncSetAttribute((const void*)cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->spmv_smem));
+    int pocc = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, cg_persistent_kernel, kSpmvThreads, h->spmv_smem));
+    pocc = std::min(pocc, env_int("B200S_SPMV_OCC", 8));
+    h->persist_grid = std::max(1, std::min(h->sm_count * std::max(1, pocc), kMaxGrid));
+  }
   int64_t n2 = std::max<int64_t>(1, p.rows / 2);
   int64_t vg = std::min<int64_t>(static_cast<int64_t>(h->sm_count) * env_int("B200S_VEC_CTAS_PER_SM", 6),
                                  (n2 + kVecThreads - 1) / kVecThreads);
@@ -796,7 +846,7 @@ void b200s_destroy(b200s_handle* h) {
     if (q != h->plan.rank && h->peer_window[q]) cudaIpcCloseMemHandle(h->peer_window[q]);
   DevBuf* bufs[] = {&h->rowptr, &h->colidx, &h->vals, &h->src, &h->tiles, &h->invdiag, &h->send_rows, &h->window,
                     &h->b, &h->r, &h->q, &h->r0, &h->s, &h->t, &h->yout, &h->scalars, &h->partials, &h->counter,
-                    &h->halo_counter, &h->history};
+                    &h->halo_counter, &h->history, &h->gridbar};
   for (DevBuf* b : bufs) dev_free(h, *b);
   if (h->hS) cudaFreeHost(h->hS);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -838,6 +888,7 @@ int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t n
   if ((rc = dev_alloc(h, h->counter, 64, true))) return rc;
   if ((rc = dev_alloc(h, h->halo_counter, 64, true))) return rc;
   if ((rc = dev_alloc(h, h->history, sizeof(double) * kHistoryCap, true))) return rc;
+  if ((rc = dev_alloc(h, h->gridbar, 256, true))) return rc;
 
   // ---- peer-visible window: 4 extended vector slots + all-reduce mailboxes + halo flags ----
   const int W = p.world;

@@ -282,6 +282,22 @@ __device__ __forceinline__ bool gated_out(const Scalars* S, int gate) {
   }
 }
 
+// Device-side timeline: time between consecutive reduction epilogues, accumulated per epilogue kind.
+__device__ __forceinline__ void timeline_mark(Scalars* S, int e) {
+  const unsigned long long now = globaltimer_ns();
+  if (e == kEpiCgInit || e == kEpiBiInit) {
+    for (int i = 0; i < 12; ++i) { S->t_phase[i] = 0; S->n_phase[i] = 0; }
+    S->t_first = now;
+    S->t_allreduce = 0;
+    S->t_halo_wait = 0;
+  } else if (e > 0 && e < 12) {
+    S->t_phase[e] += now - S->t_last;
+    S->n_phase[e]++;
+  }
+  S->t_last = now;
+  S->t_end = now;
+}
+
 // Final stage of every reduction: publish this CTA's partials, take a ticket; the last CTA folds all partials in
 // CTA order, all-reduces over ranks, runs the scalar epilogue and (in WHILE-graph mode) sets the loop condition.
 template <int NV, int THREADS>
@@ -313,22 +329,7 @@ __device__ __forceinline__ void finish_reduction(const RedCtx& ctx, double (&v)[
   if (threadIdx.x == 0) {
     *ctx.counter = 0;
     if (ctx.bump_halo) ctx.S->halo_seq++;  // this kernel carried a halo exchange: retire its sequence number
-    {
-      Scalars* S = ctx.S;
-      const unsigned long long now = globaltimer_ns();
-      const int e = ctx.epilogue;
-      if (e == kEpiCgInit || e == kEpiBiInit) {
-        for (int i = 0; i < 12; ++i) { S->t_phase[i] = 0; S->n_phase[i] = 0; }
-        S->t_first = now;
-        S->t_allreduce = 0;
-        S->t_halo_wait = 0;
-      } else if (e > 0 && e < 12) {
-        S->t_phase[e] += now - S->t_last;
-        S->n_phase[e]++;
-      }
-      S->t_last = now;
-      S->t_end = now;
-    }
+    timeline_mark(ctx.S, ctx.epilogue);
     run_epilogue(ctx, r, history);
     if (ctx.set_cond) cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(ctx.cond_handle), ctx.S->stop ? 0u : 1u);
   }
@@ -415,11 +416,19 @@ __host__ __device__ inline size_t spmv_stage_bytes(int cap_nnz, int cap_rows) {
   return up(v) + up(c) + up(r);
 }
 
-template <typename T, int LG, bool STREAM>
+// x gather: through the non-coherent path when x is read-only for the whole kernel (one product per launch), or as
+// an ordinary L1-cached load when other phases of the same (persistent) kernel rewrite x between products.
+template <bool NC, typename T>
+__device__ __forceinline__ T ldx(const T* p) {
+  if (NC) return __ldg(p);
+  return *p;
+}
+
+template <typename T, int LG, bool STREAM, bool NC>
 __device__ __forceinline__ void tile_rows_reduce(const T* __restrict__ sv, const int32_t* __restrict__ sc,
                                                  const int32_t* __restrict__ srp, int nrows, int row0, int vb0,
-                                                 int cb0, const T* __restrict__ x, T* __restrict__ y,
-                                                 const T* __restrict__ w, int tail_blk, double& d0, double& d1) {
+                                                 int cb0, const T* x, T* __restrict__ y, const T* w, int tail_blk,
+                                                 double& d0, double& d1) {
   constexpr int L = 1 << LG;
   const int lane = threadIdx.x & (L - 1);
   const int grp = threadIdx.x >> LG;
@@ -448,7 +457,7 @@ __device__ __forceinline__ void tile_rows_reduce(const T* __restrict__ sv, const
             v[j] = in ? sv[k + j * L - vb0] : T(0);
           }
 #pragma unroll
-          for (int j = 0; j < B; ++j) xv[j] = ((k + j * L) < k1) ? __ldg(x + c[j]) : T(0);
+          for (int j = 0; j < B; ++j) xv[j] = ((k + j * L) < k1) ? ldx<NC>(x + c[j]) : T(0);
 #pragma unroll
           for (int j = 0; j < B; ++j) {
             if (sizeof(T) == 4 && L == 1 && (k + j) >= kfuse)
@@ -472,72 +481,90 @@ __device__ __forceinline__ void tile_rows_reduce(const T* __restrict__ sv, const
   }
 }
 
-template <typename T, int NDOT>
-__global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArgs<T> a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full_bar[8];
-  __shared__ double red_scratch[32 * 2];
-  __shared__ T long_scratch[32];
-  if (gated_out(a.red.S, a.red.gate)) return;
+// Per-CTA state of the staged product.  `seq` counts the tiles this CTA has consumed since the mbarriers were
+// initialised, which fixes the stage (seq % stages) and the barrier parity ((seq / stages) & 1) of every tile, also
+// across successive products inside one persistent kernel.
+template <typename T>
+struct SpmvCta {
+  unsigned char* smem;
+  uint64_t* full_bar;
+  T* long_scratch;
+  size_t stage_bytes, v_bytes, c_bytes;
+  uint64_t policy;
+  unsigned seq;
+};
 
-  const int tid = threadIdx.x;
-  const size_t stage_bytes = spmv_stage_bytes<T>(a.cap_nnz, a.cap_rows);
-  const size_t v_bytes = ((static_cast<size_t>(a.cap_nnz) + 16) * sizeof(T) + 127) & ~static_cast<size_t>(127);
-  const size_t c_bytes = ((static_cast<size_t>(a.cap_nnz) + 8) * 4 + 127) & ~static_cast<size_t>(127);
-  constexpr int VA = 16 / sizeof(T);  // elements per 16-byte unit of the value array
-  const int S = a.stages;
-  const int G = gridDim.x;
-
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], 1);
+template <typename T>
+__device__ __forceinline__ void spmv_cta_init(const SpmvArgs<T>& a, SpmvCta<T>& cx, unsigned char* smem,
+                                              uint64_t* full_bar, T* long_scratch) {
+  cx.smem = smem;
+  cx.full_bar = full_bar;
+  cx.long_scratch = long_scratch;
+  cx.stage_bytes = spmv_stage_bytes<T>(a.cap_nnz, a.cap_rows);
+  cx.v_bytes = ((static_cast<size_t>(a.cap_nnz) + 16) * sizeof(T) + 127) & ~static_cast<size_t>(127);
+  cx.c_bytes = ((static_cast<size_t>(a.cap_nnz) + 8) * 4 + 127) & ~static_cast<size_t>(127);
+  cx.seq = 0;
+  cx.policy = a.evict_first ? policy_evict_first() : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+}
 
-  uint64_t policy = 0;
-  if (a.evict_first) policy = policy_evict_first();
+// One elected thread: start the bulk copies of tile t into stage s (values, column indices, row-pointer slice).
+template <typename T>
+__device__ __forceinline__ void spmv_issue(const SpmvArgs<T>& a, const SpmvCta<T>& cx, int t, int s) {
+  constexpr int VA = 16 / sizeof(T);  // elements per 16-byte unit of the value array
+  const Tile tl = a.tiles[t];
+  uint64_t* bar = &cx.full_bar[s];
+  if ((tl.meta >> 24) & kTileLong) { mbar_arrive(bar); return; }
+  const int nrows = tl.meta & 0xFFFF;
+  const int vb0 = tl.nnz0 & ~(VA - 1), vb1 = (tl.nnz0 + tl.nnz + VA - 1) & ~(VA - 1);
+  const int cb0 = tl.nnz0 & ~3, cb1 = (tl.nnz0 + tl.nnz + 3) & ~3;
+  const int rb0 = tl.row0 & ~3, rb1 = (tl.row0 + nrows + 1 + 3) & ~3;
+  const unsigned vby = static_cast<unsigned>(vb1 - vb0) * sizeof(T), cby = static_cast<unsigned>(cb1 - cb0) * 4u,
+                 rby = static_cast<unsigned>(rb1 - rb0) * 4u;
+  unsigned char* st = cx.smem + static_cast<size_t>(s) * cx.stage_bytes;
+  mbar_expect_tx(bar, vby + cby + rby);
+  if (a.evict_first) {
+    if (vby) bulk_g2s_hint(st, a.vals + vb0, vby, bar, cx.policy);
+    if (cby) bulk_g2s_hint(st + cx.v_bytes, a.colidx + cb0, cby, bar, cx.policy);
+    bulk_g2s_hint(st + cx.v_bytes + cx.c_bytes, a.rowptr + rb0, rby, bar, cx.policy);
+  } else {
+    if (vby) bulk_g2s(st, a.vals + vb0, vby, bar);
+    if (cby) bulk_g2s(st + cx.v_bytes, a.colidx + cb0, cby, bar);
+    bulk_g2s(st + cx.v_bytes + cx.c_bytes, a.rowptr + rb0, rby, bar);
+  }
+}
 
-  auto issue = [&](int t, int s) {  // thread 0 only
-    const Tile tl = a.tiles[t];
-    uint64_t* bar = &full_bar[s];
-    if ((tl.meta >> 24) & kTileLong) { mbar_arrive(bar); return; }
-    const int nrows = tl.meta & 0xFFFF;
-    const int vb0 = tl.nnz0 & ~(VA - 1), vb1 = (tl.nnz0 + tl.nnz + VA - 1) & ~(VA - 1);
-    const int cb0 = tl.nnz0 & ~3, cb1 = (tl.nnz0 + tl.nnz + 3) & ~3;
-    const int rb0 = tl.row0 & ~3, rb1 = (tl.row0 + nrows + 1 + 3) & ~3;
-    const unsigned vby = static_cast<unsigned>(vb1 - vb0) * sizeof(T), cby = static_cast<unsigned>(cb1 - cb0) * 4u,
-                   rby = static_cast<unsigned>(rb1 - rb0) * 4u;
-    unsigned char* st = smem + static_cast<size_t>(s) * stage_bytes;
-    mbar_expect_tx(bar, vby + cby + rby);
-    if (a.evict_first) {
-      if (vby) bulk_g2s_hint(st, a.vals + vb0, vby, bar, policy);
-      if (cby) bulk_g2s_hint(st + v_bytes, a.colidx + cb0, cby, bar, policy);
-      bulk_g2s_hint(st + v_bytes + c_bytes, a.rowptr + rb0, rby, bar, policy);
-    } else {
-      if (vby) bulk_g2s(st, a.vals + vb0, vby, bar);
-      if (cby) bulk_g2s(st + v_bytes, a.colidx + cb0, cby, bar);
-      bulk_g2s(st + v_bytes + c_bytes, a.rowptr + rb0, rby, bar);
+// Fill the ring with this CTA's first tiles (independent of x: may be issued long before the product starts).
+template <typename T>
+__device__ __forceinline__ void spmv_prefetch(const SpmvArgs<T>& a, const SpmvCta<T>& cx) {
+  if (threadIdx.x == 0)
+    for (int k = 0; k < a.stages; ++k) {
+      const int t = blockIdx.x + k * gridDim.x;
+      if (t < a.ntiles) spmv_issue(a, cx, t, (cx.seq + k) % a.stages);
     }
-  };
+}
 
-  if (tid == 0)
-    for (int s = 0; s < S; ++s) {
-      const int t = blockIdx.x + s * G;
-      if (t < a.ntiles) issue(t, s);
-    }
-  // multi-GPU: my boundary entries go out to the neighbours while the first tiles are in flight
-  if (a.halo.enabled) halo_push<T>(a.halo, a.red.comm, a.red.S, a.x);
-
-  double d0 = 0.0, d1 = 0.0;
+// This CTA's share of one product y = A x (+ partial dots).  spmv_prefetch must have been called for this round.
+template <typename T, int NDOT, bool NC>
+__device__ __forceinline__ void spmv_tiles(const SpmvArgs<T>& a, SpmvCta<T>& cx, double& d0, double& d1) {
+  constexpr int VA = 16 / sizeof(T);
+  const int tid = threadIdx.x;
+  const int S = a.stages;
+  const int G = gridDim.x;
   const T* w = (NDOT >= 1) ? (a.w ? a.w : a.x) : nullptr;
   bool halo_ready = (a.recv_mask == 0);
-
-  for (int it = 0;; ++it) {
-    const int t = blockIdx.x + it * G;
+  int k = 0;
+  for (;; ++k) {
+    const int t = blockIdx.x + k * G;
     if (t >= a.ntiles) break;
-    const int s = it % S;
-    const unsigned parity = (it / S) & 1;
+    const unsigned q = cx.seq + k;
+    const int s = q % S;
+    const unsigned parity = (q / S) & 1;
     const Tile tl = a.tiles[t];
     const int flags = (tl.meta >> 24) & 0xFF;
     const int nrows = tl.meta & 0xFFFF;
@@ -553,21 +580,21 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
       halo_ready = true;
     }
 
-    mbar_wait(&full_bar[s], parity);
+    mbar_wait(&cx.full_bar[s], parity);
 
     if (flags & kTileLong) {
       // one row longer than a stage: the whole CTA streams it from global memory, coalesced
       T sum = T(0);
       const int k1 = tl.nnz0 + tl.nnz;
-      for (int k = tl.nnz0 + tid; k < k1; k += kSpmvThreads)
-        sum = add_rn(sum, mul_rn(a.vals[k], __ldg(a.x + a.colidx[k])));
+      for (int kk = tl.nnz0 + tid; kk < k1; kk += kSpmvThreads)
+        sum = add_rn(sum, mul_rn(a.vals[kk], ldx<NC>(a.x + a.colidx[kk])));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum = add_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
       __syncthreads();
-      if ((tid & 31) == 0) long_scratch[tid >> 5] = sum;
+      if ((tid & 31) == 0) cx.long_scratch[tid >> 5] = sum;
       __syncthreads();
       if (tid < 32) {
-        sum = (tid < kSpmvThreads / 32) ? long_scratch[tid] : T(0);
+        sum = (tid < kSpmvThreads / 32) ? cx.long_scratch[tid] : T(0);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum = add_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
         if (tid == 0) {
@@ -578,43 +605,62 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
         }
       }
     } else {
-      unsigned char* st = smem + static_cast<size_t>(s) * stage_bytes;
+      unsigned char* st = cx.smem + static_cast<size_t>(s) * cx.stage_bytes;
       T* sv = reinterpret_cast<T*>(st);
-      const int32_t* sc = reinterpret_cast<const int32_t*>(st + v_bytes);
-      const int32_t* srp = reinterpret_cast<const int32_t*>(st + v_bytes + c_bytes) + (tl.row0 - (tl.row0 & ~3));
+      const int32_t* sc = reinterpret_cast<const int32_t*>(st + cx.v_bytes);
+      const int32_t* srp = reinterpret_cast<const int32_t*>(st + cx.v_bytes + cx.c_bytes) + (tl.row0 - (tl.row0 & ~3));
       const int vb0 = tl.nnz0 & ~(VA - 1);
       const int cb0 = tl.nnz0 & ~3;
       if (flags & kTileStream) {
         // phase 1: products, perfectly balanced over the CTA (CSR-stream); phase 2 sums them per row
         const int k1 = tl.nnz0 + tl.nnz;
-        for (int k = tl.nnz0 + tid; k < k1; k += kSpmvThreads)
-          sv[k - vb0] = mul_rn(sv[k - vb0], __ldg(a.x + sc[k - cb0]));
+        for (int kk = tl.nnz0 + tid; kk < k1; kk += kSpmvThreads)
+          sv[kk - vb0] = mul_rn(sv[kk - vb0], ldx<NC>(a.x + sc[kk - cb0]));
         __syncthreads();
         switch (lg) {
-          case 0: tile_rows_reduce<T, 0, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 1: tile_rows_reduce<T, 1, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 2: tile_rows_reduce<T, 2, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 3: tile_rows_reduce<T, 3, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 4: tile_rows_reduce<T, 4, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          default: tile_rows_reduce<T, 5, true>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 0: tile_rows_reduce<T, 0, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 1: tile_rows_reduce<T, 1, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 2: tile_rows_reduce<T, 2, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 3: tile_rows_reduce<T, 3, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 4: tile_rows_reduce<T, 4, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          default: tile_rows_reduce<T, 5, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
         }
       } else {
         switch (lg) {
-          case 0: tile_rows_reduce<T, 0, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, a.tail_blk, d0, d1); break;
-          case 1: tile_rows_reduce<T, 1, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 2: tile_rows_reduce<T, 2, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 3: tile_rows_reduce<T, 3, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 4: tile_rows_reduce<T, 4, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          default: tile_rows_reduce<T, 5, false>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 0: tile_rows_reduce<T, 0, false, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, a.tail_blk, d0, d1); break;
+          case 1: tile_rows_reduce<T, 1, false, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 2: tile_rows_reduce<T, 2, false, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 3: tile_rows_reduce<T, 3, false, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          case 4: tile_rows_reduce<T, 4, false, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+          default: tile_rows_reduce<T, 5, false, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
         }
       }
     }
     __syncthreads();  // every thread is done with stage s
     if (tid == 0) {
       const int t2 = t + S * G;
-      if (t2 < a.ntiles) issue(t2, s);
+      if (t2 < a.ntiles) spmv_issue(a, cx, t2, s);
     }
   }
+  cx.seq += k;
+}
+
+template <typename T, int NDOT>
+__global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArgs<T> a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[8];
+  __shared__ double red_scratch[32 * 2];
+  __shared__ T long_scratch[32];
+  if (gated_out(a.red.S, a.red.gate)) return;
+
+  SpmvCta<T> cx;
+  spmv_cta_init(a, cx, smem, full_bar, long_scratch);
+  spmv_prefetch(a, cx);
+  // multi-GPU: my boundary entries go out to the neighbours while the first tiles are in flight
+  if (a.halo.enabled) halo_push<T>(a.halo, a.red.comm, a.red.S, a.x);
+
+  double d0 = 0.0, d1 = 0.0;
+  spmv_tiles<T, NDOT, true>(a, cx, d0, d1);
 
   if (a.red.epilogue != kEpiNone) {
     if (NDOT == 0) {
@@ -762,11 +808,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const VecArgs a) {
 }
 
 // CG :74-84 in one pass: x += alpha p; r -= alpha Ap; z = D^-1 r (not stored); ||r||^2; r.z
-__global__ void __launch_bounds__(kVecThreads) cg_update_kernel(const VecArgs a) {
-  __shared__ double scratch[32 * 2];
-  if (gated_out(a.red.S, a.red.gate)) return;
-  const double alpha = a.red.S->alpha;
-  double v[2] = {0.0, 0.0};
+__device__ __forceinline__ void cg_update_body(const VecArgs& a, const double alpha, double (&v)[2]) {
   vec_loop(a.n,
     [&](long long i2) {
       double2 x = ld2(a.x, i2), r = ld2(a.r, i2);
@@ -785,13 +827,18 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_kernel(const VecArgs a)
       const double z = a.invdiag[i] * r;
       v[0] = fma_rn(r, r, v[0]); v[1] = fma_rn(r, z, v[1]);
     });
+}
+
+__global__ void __launch_bounds__(kVecThreads) cg_update_kernel(const VecArgs a) {
+  __shared__ double scratch[32 * 2];
+  if (gated_out(a.red.S, a.red.gate)) return;
+  double v[2] = {0.0, 0.0};
+  cg_update_body(a, a.red.S->alpha, v);
   finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
 }
 
 // CG :81,:86: p = D^-1 r + beta p
-__global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgs a) {
-  if (gated_out(a.red.S, a.red.gate)) return;
-  const double beta = a.red.S->beta;
+__device__ __forceinline__ void cg_direction_body(const VecArgs& a, const double beta) {
   vec_loop(a.n,
     [&](long long i2) {
       const double2 r = ld2(a.r, i2), d = ld2(a.invdiag, i2);
@@ -800,6 +847,11 @@ __global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgs
       st2(a.p, i2, p);
     },
     [&](long long i) { a.p[i] = fma_rn(beta, a.p[i], a.invdiag[i] * a.r[i]); });
+}
+
+__global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgs a) {
+  if (gated_out(a.red.S, a.red.gate)) return;
+  cg_direction_body(a, a.red.S->beta);
 }
 
 // BiCGSTAB start (BiCGSTAB.h:42-46): r = b - A x0 (t holds A x0), r0 = r, ||b||^2, ||r||^2; v = p = 0 (:56)
@@ -921,6 +973,142 @@ __global__ void __launch_bounds__(kVecThreads) finalize_kernel(const VecArgs a) 
 // Sets the WHILE condition from the control state (used after the init phase and by chunk boundaries).
 __global__ void set_condition_kernel(const Scalars* S, unsigned long long handle) {
   cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(handle), S->stop ? 0u : 1u);
+}
+
+
+// ------------------------------------------------------------------------------------- persistent CG (one launch)
+// The whole loop of ConjugateGradient.h:69-88 in ONE cooperative kernel: the three passes of an iteration are phases
+// separated by grid-wide barriers instead of kernel boundaries, and the reductions ride on the barriers (the CTA
+// that arrives last folds the partials, all-reduces over ranks, runs the scalar epilogue, then releases everybody).
+// Same device functions, same arithmetic and the same reduction order as the three-kernel pipeline, so results are
+// bit-identical to the graph modes; what disappears is launch latency, which dominates when an iteration is tens of
+// microseconds (strong scaling over 8 GPUs, L2-sized problems).
+struct CgPersistArgs {
+  SpmvArgs<double> sp;
+  VecArgs ve;
+  unsigned int* bar_count;
+  unsigned int* bar_gen;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid barrier; with NV > 0 also a deterministic reduction of v over CTAs and ranks followed by the epilogue.
+template <int NV, int THREADS>
+__device__ __forceinline__ void grid_sync(const RedCtx& ctx, double* v, double* scratch, double* history,
+                                          unsigned* bar_count, unsigned* bar_gen, unsigned& gen) {
+  __shared__ int s_last_g;
+  if (NV > 0) {
+    double t[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) t[j] = v[j];
+    block_reduce<(NV > 0 ? NV : 1), THREADS>(t, scratch);
+    if (threadIdx.x == 0)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) ctx.partials[blockIdx.x * 4 + j] = t[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned ticket = atomicAdd(bar_count, 1u);
+    s_last_g = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last_g) {
+    double r[4] = {0, 0, 0, 0};
+    if (NV > 0) {
+      __threadfence();
+      double t[NV > 0 ? NV : 1];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) t[j] = 0.0;
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += THREADS)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) t[j] += __ldcg(ctx.partials + b * 4 + j);
+      block_reduce<(NV > 0 ? NV : 1), THREADS>(t, scratch);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) r[j] = t[j];
+      allreduce_ranks(ctx.comm, ctx.S, r, NV);
+    }
+    if (threadIdx.x == 0) {
+      *bar_count = 0;
+      if (NV > 0) {
+        if (ctx.bump_halo) ctx.S->halo_seq++;
+        timeline_mark(ctx.S, ctx.epilogue);
+        run_epilogue(ctx, r, history);
+      }
+      __threadfence();
+      st_release_gpu(bar_gen, gen + 1);
+    }
+  } else if (threadIdx.x == 0) {
+    while (ld_acquire_gpu(bar_gen) != gen + 1) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  ++gen;
+}
+
+__global__ void __launch_bounds__(kSpmvThreads, 4) cg_persistent_kernel(const CgPersistArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[8];
+  __shared__ double red_scratch[32 * 2];
+  __shared__ double long_scratch[32];
+  Scalars* S = a.sp.red.S;
+  SpmvCta<double> cx;
+  spmv_cta_init(a.sp, cx, smem, full_bar, long_scratch);
+  unsigned gen = __ldcg(a.bar_gen);  // stable: only barriers of THIS kernel advance it, and nobody has arrived yet
+  // every CTA must have read `gen` before anyone can release the first barrier: guaranteed, because a release needs
+  // all CTAs to arrive, and each arrives after this read.
+  RedCtx red_pap = a.sp.red;
+  red_pap.epilogue = kEpiCgPAp;
+  red_pap.bump_halo = a.sp.halo.enabled;
+  RedCtx red_upd = a.ve.red;
+  red_upd.epilogue = kEpiCgUpdate;
+  red_upd.bump_halo = 0;
+  RedCtx red_none = a.ve.red;
+  red_none.epilogue = kEpiNone;
+
+  bool first = true, pending = false;
+  if (!__ldcg(&S->stop)) {
+    spmv_prefetch(a.sp, cx);
+    pending = true;
+  }
+  // S changes only inside barrier epilogues, so after every barrier all CTAs read the same control state
+  while (!__ldcg(&S->stop)) {
+    if (!first) {
+      cg_direction_body(a.ve, __ldcg(&S->beta));
+      grid_sync<0, kSpmvThreads>(red_none, nullptr, red_scratch, a.ve.history, a.bar_count, a.bar_gen, gen);
+    }
+    first = false;
+    if (a.sp.halo.enabled) halo_push<double>(a.sp.halo, a.sp.red.comm, S, a.sp.x);
+    double d0 = 0.0, d1 = 0.0;
+    spmv_tiles<double, 1, false>(a.sp, cx, d0, d1);
+    spmv_prefetch(a.sp, cx);  // the next product's first tiles fly during the two vector phases
+    {
+      double v[1] = {d0};
+      grid_sync<1, kSpmvThreads>(red_pap, v, red_scratch, a.ve.history, a.bar_count, a.bar_gen, gen);
+    }
+    {
+      double v[2] = {0.0, 0.0};
+      cg_update_body(a.ve, __ldcg(&S->alpha), v);
+      grid_sync<2, kSpmvThreads>(red_upd, v, red_scratch, a.ve.history, a.bar_count, a.bar_gen, gen);
+    }
+  }
+  if (pending) {  // tiles prefetched for a product that will not happen: wait until the copies have landed
+    for (int k = 0; k < a.sp.stages; ++k) {
+      const int t = blockIdx.x + k * gridDim.x;
+      if (t < a.sp.ntiles) {
+        const unsigned q = cx.seq + k;
+        mbar_wait(&full_bar[q % a.sp.stages], (q / a.sp.stages) & 1);
+      }
+    }
+  }
 }
 
 }  // namespace b200s

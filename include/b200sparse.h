@@ -51,7 +51,13 @@ typedef enum {
 enum { B200S_LOWER = 1, B200S_UPPER = 2, B200S_BOTH = 3 };
 enum { B200S_PRECOND_IDENTITY = 0, B200S_PRECOND_JACOBI = 1 };
 enum { B200S_SPMV_AUTO = 0, B200S_SPMV_STAGED = 1, B200S_SPMV_DIRECT = 2 };
-enum { B200S_LOOP_AUTO = 0, B200S_LOOP_WHILE_GRAPH = 1, B200S_LOOP_CHUNKED_GRAPH = 2, B200S_LOOP_STREAM = 3 };
+enum {
+  B200S_LOOP_AUTO = 0,
+  B200S_LOOP_WHILE_GRAPH = 1,   /* one graph launch; WHILE node iterates on a device-side condition */
+  B200S_LOOP_CHUNKED_GRAPH = 2, /* graphs of chunk_iters unrolled iterations; host polls the stop flag per chunk */
+  B200S_LOOP_STREAM = 3,        /* plain stream launches, host polls per iteration (debug / profiling) */
+  B200S_LOOP_PERSISTENT = 4     /* CG only: the whole loop in one cooperative kernel (grid barriers); BiCGSTAB uses WHILE */
+};
 
 /* Host-provided all-gather used ONLY while building the multi-GPU plan (setup, never in the iteration):
  * every rank contributes `bytes` bytes from `send`; `recv` receives world*bytes, ordered by rank.  Return 0 on

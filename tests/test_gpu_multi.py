@@ -14,9 +14,11 @@ def _gpus():
 
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("name", ["poisson3d", "convdiff3d", "powerlaw"])
-def test_row_partitioned_solvers(world, name):
+@pytest.mark.parametrize("loop_mode", [1, 4])
+def test_row_partitioned_solvers(world, name, loop_mode, monkeypatch):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("B200S_LOOP_MODE", str(loop_mode))  # 1 = WHILE graph, 4 = persistent cooperative CG kernel
     res = launch(world, "gpu", name, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-5000:]
     assert res.stdout.count("gpu ok") == world

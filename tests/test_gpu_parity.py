@@ -119,15 +119,22 @@ def test_solver_golden(case, golden, egm):
 
 @pytest.mark.parametrize("case", ["cg/varcoef3d_10/uplo3_pre1", "bicgstab/convdiff3d_10_g0.5/pre1",
                                   "cg/poisson2d_24/guess", "bicgstab/random_square_90/ones"])
-@pytest.mark.parametrize("loop_mode", [1, 2, 3])
+@pytest.mark.parametrize("loop_mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("impl", [1, 2])
 def test_loop_modes_and_spmv_impls_agree(case, loop_mode, impl, golden, egm):
-    """WHILE-graph, chunked-graph and plain-stream loops run the same kernels: results must be bit-identical, and
-    every combination must meet the parity bar."""
+    """WHILE-graph, chunked-graph, plain-stream and persistent-kernel loops run the same device functions: results
+    must be bit-identical, and every combination must meet the parity bar."""
     base = _solve(egm, golden, case, loop_mode=1, spmv_impl=impl)
     other = _solve(egm, golden, case, loop_mode=loop_mode, spmv_impl=impl, chunk_iters=7)
     assert np.array_equal(base[0], other[0]) and base[1:4] == other[1:4]
     _check(case, golden, *other)
+
+
+@pytest.mark.parametrize("case", golden_case_names("cg"))
+def test_persistent_cg_golden(case, golden, egm):
+    """Every CG golden case through the one-launch persistent kernel (B200S_LOOP_PERSISTENT)."""
+    x, it, err, info, tol = _solve(egm, golden, case, loop_mode=4)
+    _check(case, golden, x, it, err, info, tol)
 
 
 def test_determinism_bitwise_reruns(golden, egm):
