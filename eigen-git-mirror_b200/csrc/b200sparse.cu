@@ -69,6 +69,7 @@ struct b200s_handle {
   Scalars* hS = nullptr;  // pinned mirror
   // launch geometry
   int spmv_grid = 0, spmv_stages = 0, spmv_smem = 0, vec_grid = 0;
+  int spmv_grid_f32 = 0, spmv_smem_f32 = 0;  // float tiles are smaller: more CTAs fit per SM
   int evict_first = 0;
   GraphSet cg, bicg;
   size_t device_bytes = 0;
@@ -233,7 +234,8 @@ int make_spmv_args(b200s_handle* h, SpmvArgs<T>& a, const T* x_ext, T* y, const 
     if (epilogue == kEpiNone) epilogue = kEpiSpmvOnly;  // the final rendezvous retires the halo sequence number
     a.halo.enabled = 1;
     {
-      const int grid = (h->spmv_impl == B200S_SPMV_DIRECT) ? h->sm_count * 8 : h->spmv_grid;
+      const int grid = (h->spmv_impl == B200S_SPMV_DIRECT) ? h->sm_count * 8
+                                                           : (sizeof(T) == 4 ? h->spmv_grid_f32 : h->spmv_grid);
       const int64_t total = static_cast<int64_t>(h->plan.send_rows.size());
       a.halo.npush = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(grid, (total + 2047) / 2048)));
     }
@@ -272,9 +274,11 @@ int launch_spmv_args(b200s_handle* h, const SpmvArgs<T>& a, int ndot) {
     }
 #undef B200S_DIRECT
   } else {
-    if (ndot == 0) spmv_staged_kernel<T, 0><<<h->spmv_grid, kSpmvThreads, h->spmv_smem, h->stream>>>(a);
-    else if (ndot == 1) spmv_staged_kernel<T, 1><<<h->spmv_grid, kSpmvThreads, h->spmv_smem, h->stream>>>(a);
-    else spmv_staged_kernel<T, 2><<<h->spmv_grid, kSpmvThreads, h->spmv_smem, h->stream>>>(a);
+    const int grid = sizeof(T) == 4 ? h->spmv_grid_f32 : h->spmv_grid;
+    const int smem = sizeof(T) == 4 ? h->spmv_smem_f32 : h->spmv_smem;
+    if (ndot == 0) spmv_staged_kernel<T, 0><<<grid, kSpmvThreads, smem, h->stream>>>(a);
+    else if (ndot == 1) spmv_staged_kernel<T, 1><<<grid, kSpmvThreads, smem, h->stream>>>(a);
+    else spmv_staged_kernel<T, 2><<<grid, kSpmvThreads, smem, h->stream>>>(a);
   }
   CK(cudaGetLastError());
   h->last_launches++;
@@ -339,7 +343,7 @@ int launch_cg_persistent(b200s_handle* h) {
   if (a.sp.halo.enabled) a.sp.halo.npush = std::min(a.sp.halo.npush, h->persist_grid);
   a.ve = make_vec(h, kEpiCgUpdate, kGateNone, false, 0);
   a.bar_count = h->gridbar.as<unsigned>();
-  a.bar_gen = h->gridbar.as<unsigned>() + 32;
+  a.bar_gen = h->gridbar.as<unsigned>() + 1024;  // 4 KB away from the arrival counter: a different L2 slice
   void* params[] = {&a};
   CK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(h->persist_grid), dim3(kSpmvThreads), params,
                                  static_cast<size_t>(h->spmv_smem), h->stream));
@@ -730,11 +734,13 @@ int configure_spmv(b200s_handle* h) {
   if (stage * stages > 220 * 1024) return fail(h, B200S_ERR_INVALID, "tile_nnz/tile_rows too large for shared memory");
   h->spmv_stages = stages;
   h->spmv_smem = static_cast<int>(stage * stages);
-  const void* fns[] = {
-      (const void*)spmv_staged_kernel<double, 0>, (const void*)spmv_staged_kernel<double, 1>,
-      (const void*)spmv_staged_kernel<double, 2>, (const void*)spmv_staged_kernel<float, 0>,
-      (const void*)spmv_staged_kernel<float, 1>,  (const void*)spmv_staged_kernel<float, 2>};
+  h->spmv_smem_f32 = static_cast<int>(spmv_stage_bytes<float>(p.tile_nnz, p.tile_rows_cap) * stages);
+  const void* fns[] = {(const void*)spmv_staged_kernel<double, 0>, (const void*)spmv_staged_kernel<double, 1>,
+                       (const void*)spmv_staged_kernel<double, 2>};
+  const void* fns32[] = {(const void*)spmv_staged_kernel<float, 0>, (const void*)spmv_staged_kernel<float, 1>,
+                         (const void*)spmv_staged_kernel<float, 2>};
   for (const void* f : fns) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, h->spmv_smem));
+  for (const void* f : fns32) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, h->spmv_smem_f32));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_staged_kernel<double, 1>, kSpmvThreads, h->spmv_smem));
   if (occ < 1) return fail(h, B200S_ERR_CUDA, "staged SpMV kernel does not fit on an SM");
@@ -743,6 +749,12 @@ int configure_spmv(b200s_handle* h) {
   int ntiles = static_cast<int>(p.tiles.size());
   grid = std::max(1, std::min(grid, std::max(1, ntiles)));
   h->spmv_grid = std::min(grid, kMaxGrid);
+  {
+    int occ32 = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, spmv_staged_kernel<float, 1>, kSpmvThreads, h->spmv_smem_f32));
+    occ32 = std::max(1, std::min(occ32, env_int("B200S_SPMV_OCC", 8)));
+    h->spmv_grid_f32 = std::min(std::max(1, std::min(h->sm_count * occ32, std::max(1, ntiles))), kMaxGrid);
+  }
   {
     CK(cudaFuncSetAttribute((const void*)cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->spmv_smem));
     int pocc = 0;
@@ -888,7 +900,7 @@ int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t n
   if ((rc = dev_alloc(h, h->counter, 64, true))) return rc;
   if ((rc = dev_alloc(h, h->halo_counter, 64, true))) return rc;
   if ((rc = dev_alloc(h, h->history, sizeof(double) * kHistoryCap, true))) return rc;
-  if ((rc = dev_alloc(h, h->gridbar, 256, true))) return rc;
+  if ((rc = dev_alloc(h, h->gridbar, 8192, true))) return rc;
 
   // ---- peer-visible window: 4 extended vector slots + all-reduce mailboxes + halo flags ----
   const int W = p.world;

@@ -769,13 +769,29 @@ struct VecArgs {
 // taken by thread 0 of CTA 0.  f2(i2) handles elements 2*i2 and 2*i2+1, f1(i) a single element.
 template <typename F2, typename F1>
 __device__ __forceinline__ void vec_loop(long long n, F2 f2, F1 f1) {
+  // Two pairs per thread and trip: twice the bytes in flight per thread (the order in which a thread visits its
+  // elements, hence every reduction, is unchanged).
+  constexpr int U = 2;
   const long long n2 = n >> 1;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i2 < n2; i2 += stride) f2(i2);
+  for (long long i2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i2 < n2; i2 += U * stride) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i2 + u * stride < n2) f2(i2 + u * stride);
+  }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) f1(n - 1);
 }
 
-__device__ __forceinline__ double2 ld2(const double* p, long long i2) { return reinterpret_cast<const double2*>(p)[i2]; }
+// Streaming 128-bit load: the vector passes touch every element exactly once, so lines are not allocated in L1
+// (in the persistent kernel L1 is only what the 4 x 52 KB shared-memory rings leave over).
+__device__ __forceinline__ double2 ld2(const double* p, long long i2) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+               : "=d"(v.x), "=d"(v.y)
+               : "l"(reinterpret_cast<const double2*>(p) + i2)
+               : "memory");
+  return v;
+}
 __device__ __forceinline__ void st2(double* p, long long i2, double2 v) { reinterpret_cast<double2*>(p)[i2] = v; }
 
 // CG start (ConjugateGradient.h:43-67): r = b - A x0 (q holds A x0 when there is a guess, else r = b),
@@ -808,8 +824,10 @@ __global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const VecArgs a) {
 }
 
 // CG :74-84 in one pass: x += alpha p; r -= alpha Ap; z = D^-1 r (not stored); ||r||^2; r.z
-__device__ __forceinline__ void cg_update_body(const VecArgs& a, const double alpha, double (&v)[2]) {
-  vec_loop(a.n,
+__device__ __forceinline__ void cg_update_body(const VecArgs& av, const double alpha, double (&v)[2]) {
+  struct { double* __restrict__ x; double* __restrict__ r; const double* __restrict__ p; const double* __restrict__ q;
+           const double* __restrict__ invdiag; } a = {av.x, av.r, av.p, av.q, av.invdiag};
+  vec_loop(av.n,
     [&](long long i2) {
       double2 x = ld2(a.x, i2), r = ld2(a.r, i2);
       const double2 p = ld2(a.p, i2), q = ld2(a.q, i2), d = ld2(a.invdiag, i2);
@@ -838,8 +856,10 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_kernel(const VecArgs a)
 }
 
 // CG :81,:86: p = D^-1 r + beta p
-__device__ __forceinline__ void cg_direction_body(const VecArgs& a, const double beta) {
-  vec_loop(a.n,
+__device__ __forceinline__ void cg_direction_body(const VecArgs& av, const double beta) {
+  struct { double* __restrict__ p; const double* __restrict__ r; const double* __restrict__ invdiag; } a = {av.p, av.r,
+                                                                                                        av.invdiag};
+  vec_loop(av.n,
     [&](long long i2) {
       const double2 r = ld2(a.r, i2), d = ld2(a.invdiag, i2);
       double2 p = ld2(a.p, i2);
@@ -1046,8 +1066,7 @@ __device__ __forceinline__ void grid_sync(const RedCtx& ctx, double* v, double* 
       st_release_gpu(bar_gen, gen + 1);
     }
   } else if (threadIdx.x == 0) {
-    while (ld_acquire_gpu(bar_gen) != gen + 1) {
-    }
+    while (ld_acquire_gpu(bar_gen) != gen + 1) __nanosleep(40);  // back off: 591 pollers share one L2 line
     __threadfence();
   }
   __syncthreads();
