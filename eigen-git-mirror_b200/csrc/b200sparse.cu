@@ -37,7 +37,7 @@ struct GraphSet {
   cudaGraphExec_t exec = nullptr;
   cudaGraph_t body_graph = nullptr;   // chunked mode: the unrolled body
   cudaGraphExec_t body_exec = nullptr;
-  int init_kernels = 0, body_kernels = 0, tail_kernels = 0;
+  int init_kernels = 0, body_kernels = 0, tail_kernels = 0, body_unroll = 1;
   bool built = false;
 };
 
@@ -71,6 +71,8 @@ struct b200s_handle {
   int spmv_grid = 0, spmv_stages = 0, spmv_smem = 0, vec_grid = 0;
   int spmv_grid_f32 = 0, spmv_smem_f32 = 0;  // float tiles are smaller: more CTAs fit per SM
   int evict_first = 0;
+  int pdl = 0;           // programmatic dependent launch between the solver kernels (B200S_PDL=1)
+  int body_unroll = 1;   // iterations per WHILE-body (amortises the loop-back, keeps PDL edges inside the body)
   GraphSet cg, bicg;
   size_t device_bytes = 0;
   // stats of the last call
@@ -193,6 +195,24 @@ unsigned recv_mask(const b200s_handle* h) {
 }
 
 // ---- kernel launch helpers (all on h->stream; counted) ----
+// Solver kernels are launched with programmatic stream serialization (PDL): a kernel may become resident and run its
+// data-independent prologue (mbarrier setup, the first tile copies of the SpMV) while its predecessor drains; every
+// kernel executes griddepcontrol.wait before it touches anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(b200s_handle* h, void (*kernel)(KArgs...), int grid, int block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = h->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // `halo_slot` >= 0: x_ext is that extended slot of the peer-visible window and its boundary entries are pushed to the
 // neighbours at the head of the kernel (multi-GPU only).
 template <typename T>
@@ -261,24 +281,24 @@ int launch_spmv_args(b200s_handle* h, const SpmvArgs<T>& a, int ndot) {
     const int grid = h->sm_count * 8;
 #define B200S_DIRECT(LG)                                                                                   \
   case LG:                                                                                                 \
-    if (ndot == 0) spmv_direct_kernel<T, LG, 0><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);            \
-    else if (ndot == 1) spmv_direct_kernel<T, LG, 1><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);       \
-    else spmv_direct_kernel<T, LG, 2><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);                      \
+    if (ndot == 0) launch_k(h, spmv_direct_kernel<T, LG, 0>, grid, kSpmvThreads, 0, a, rows);            \
+    else if (ndot == 1) launch_k(h, spmv_direct_kernel<T, LG, 1>, grid, kSpmvThreads, 0, a, rows);       \
+    else launch_k(h, spmv_direct_kernel<T, LG, 2>, grid, kSpmvThreads, 0, a, rows);                      \
     break;
     switch (h->direct_lg) {
       B200S_DIRECT(0) B200S_DIRECT(1) B200S_DIRECT(2) B200S_DIRECT(3) B200S_DIRECT(4)
       default:
-        if (ndot == 0) spmv_direct_kernel<T, 5, 0><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);
-        else if (ndot == 1) spmv_direct_kernel<T, 5, 1><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);
-        else spmv_direct_kernel<T, 5, 2><<<grid, kSpmvThreads, 0, h->stream>>>(a, rows);
+        if (ndot == 0) launch_k(h, spmv_direct_kernel<T, 5, 0>, grid, kSpmvThreads, 0, a, rows);
+        else if (ndot == 1) launch_k(h, spmv_direct_kernel<T, 5, 1>, grid, kSpmvThreads, 0, a, rows);
+        else launch_k(h, spmv_direct_kernel<T, 5, 2>, grid, kSpmvThreads, 0, a, rows);
     }
 #undef B200S_DIRECT
   } else {
     const int grid = sizeof(T) == 4 ? h->spmv_grid_f32 : h->spmv_grid;
     const int smem = sizeof(T) == 4 ? h->spmv_smem_f32 : h->spmv_smem;
-    if (ndot == 0) spmv_staged_kernel<T, 0><<<grid, kSpmvThreads, smem, h->stream>>>(a);
-    else if (ndot == 1) spmv_staged_kernel<T, 1><<<grid, kSpmvThreads, smem, h->stream>>>(a);
-    else spmv_staged_kernel<T, 2><<<grid, kSpmvThreads, smem, h->stream>>>(a);
+    if (ndot == 0) launch_k(h, spmv_staged_kernel<T, 0>, grid, kSpmvThreads, smem, a);
+    else if (ndot == 1) launch_k(h, spmv_staged_kernel<T, 1>, grid, kSpmvThreads, smem, a);
+    else launch_k(h, spmv_staged_kernel<T, 2>, grid, kSpmvThreads, smem, a);
   }
   CK(cudaGetLastError());
   h->last_launches++;
@@ -306,7 +326,7 @@ VecArgs make_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGra
 
 #define LAUNCH_VEC(kernel, args)                                     \
   do {                                                               \
-    kernel<<<h->vec_grid, kVecThreads, 0, h->stream>>>(args);        \
+    launch_k(h, kernel, h->vec_grid, kVecThreads, 0, args);          \
     CK(cudaGetLastError());                                          \
     h->last_launches++;                                              \
   } while (0)
@@ -433,8 +453,11 @@ int build_graphs(b200s_handle* h, GraphSet& g, enqueue_fn init, enqueue_fn body)
     cudaGraph_t body_graph = np.conditional.phGraph_out[0];
     CK(cudaStreamBeginCaptureToGraph(h->stream, body_graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     h->last_launches = 0;
-    rc = body(h, true, cond);
-    g.body_kernels = static_cast<int>(h->last_launches);
+    // several gated iterations per pass of the WHILE node: only the last one's epilogue has to set the condition
+    // (a stop raised earlier leaves it untouched and simply gates the remaining kernels of the pass off)
+    for (int u = 0; u < h->body_unroll && !rc; ++u) rc = body(h, true, cond);
+    g.body_kernels = static_cast<int>(h->last_launches) / h->body_unroll;
+    g.body_unroll = h->body_unroll;
     ee = cudaStreamEndCapture(h->stream, &tmp);
     if (rc) return rc;
     CK(ee);
@@ -576,7 +599,10 @@ int run_solve(b200s_handle* h, bool bicg, const double* b_dev, double* x_dev, in
     if (bicg) init_spmv = 1;  // counted by kEpiBiInit regardless (the gated launch still happens)
     int64_t loop_spmv = std::max<int64_t>(0, S.spmv_count - init_spmv);
     int64_t passes = bicg ? (loop_spmv - S.restarts + 1) / 2 : loop_spmv;
-    h->last_launches = g.init_kernels + passes * g.body_kernels + g.tail_kernels;
+    // the WHILE node runs whole passes of body_unroll iterations; kernels of iterations past the stop are launched
+    // too (they return at their gate)
+    int64_t wpasses = (passes + g.body_unroll - 1) / g.body_unroll;
+    h->last_launches = g.init_kernels + wpasses * g.body_unroll * g.body_kernels + g.tail_kernels;
   }
   return 0;
 }
@@ -842,6 +868,10 @@ int b200s_create(const b200s_config* cfg, b200s_handle** out) {
   h->loop_mode = h->cfg.loop_mode ? h->cfg.loop_mode : env_int("B200S_LOOP_MODE", B200S_LOOP_WHILE_GRAPH);
   h->spmv_impl = h->cfg.spmv_impl ? h->cfg.spmv_impl : env_int("B200S_SPMV_IMPL", B200S_SPMV_STAGED);
   h->evict_first = env_int("B200S_EVICT_FIRST", 0);
+  // measured (profiles/r1_loop_overheads.txt): PDL with an early trigger lets dependent CTAs squat on registers and
+  // shared memory and slows the 256^3 iteration by 7 %; it only pays below 64^3.  Off by default.
+  h->pdl = env_int("B200S_PDL", 0);
+  h->body_unroll = std::max(1, std::min(16, env_int("B200S_BODY_UNROLL", 4)));
   if (h->cfg.tile_nnz <= 0) h->cfg.tile_nnz = env_int("B200S_TILE_NNZ", 0);
   if (h->cfg.tile_rows <= 0) h->cfg.tile_rows = env_int("B200S_TILE_ROWS", 0);
   *out = h;

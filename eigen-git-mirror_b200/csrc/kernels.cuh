@@ -68,6 +68,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// Programmatic dependent launch: let the next kernel of the stream become resident early / wait until everything the
+// previous kernel wrote is visible.  Both are no-ops for launches without the PDL attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -651,11 +656,18 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
   __shared__ uint64_t full_bar[8];
   __shared__ double red_scratch[32 * 2];
   __shared__ T long_scratch[32];
-  if (gated_out(a.red.S, a.red.gate)) return;
-
+  // Prologue that does not depend on the previous kernel: barrier setup and the first tile copies (matrix data is
+  // constant).  It overlaps the predecessor's tail under programmatic dependent launch.
+  pdl_launch_dependents();
   SpmvCta<T> cx;
   spmv_cta_init(a, cx, smem, full_bar, long_scratch);
   spmv_prefetch(a, cx);
+  pdl_wait();
+  if (gated_out(a.red.S, a.red.gate)) {  // loop already stopped: let the copies land, then leave
+    for (int k = 0; k < a.stages; ++k)
+      if (static_cast<int>(blockIdx.x + k * gridDim.x) < a.ntiles) mbar_wait(&full_bar[k], 0);
+    return;
+  }
   // multi-GPU: my boundary entries go out to the neighbours while the first tiles are in flight
   if (a.halo.enabled) halo_push<T>(a.halo, a.red.comm, a.red.S, a.x);
 
@@ -681,6 +693,8 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
 template <typename T, int LG, int NDOT>
 __global__ void __launch_bounds__(kSpmvThreads) spmv_direct_kernel(const SpmvArgs<T> a, int rows) {
   __shared__ double red_scratch[32 * 2];
+  pdl_launch_dependents();
+  pdl_wait();
   if (gated_out(a.red.S, a.red.gate)) return;
   constexpr int L = 1 << LG;
   const int lane = threadIdx.x & (L - 1);
@@ -797,6 +811,8 @@ __device__ __forceinline__ void st2(double* p, long long i2, double2 v) { reinte
 // CG start (ConjugateGradient.h:43-67): r = b - A x0 (q holds A x0 when there is a guess, else r = b),
 // p = D^-1 r, and the three reductions ||b||^2, ||r||^2, r.p in the same pass.
 __global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const VecArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32 * 3];
   const bool guess = a.red.S->use_guess != 0;
   double v[3] = {0.0, 0.0, 0.0};
@@ -848,6 +864,8 @@ __device__ __forceinline__ void cg_update_body(const VecArgs& av, const double a
 }
 
 __global__ void __launch_bounds__(kVecThreads) cg_update_kernel(const VecArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32 * 2];
   if (gated_out(a.red.S, a.red.gate)) return;
   double v[2] = {0.0, 0.0};
@@ -870,12 +888,16 @@ __device__ __forceinline__ void cg_direction_body(const VecArgs& av, const doubl
 }
 
 __global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (gated_out(a.red.S, a.red.gate)) return;
   cg_direction_body(a, a.red.S->beta);
 }
 
 // BiCGSTAB start (BiCGSTAB.h:42-46): r = b - A x0 (t holds A x0), r0 = r, ||b||^2, ||r||^2; v = p = 0 (:56)
 __global__ void __launch_bounds__(kVecThreads) bicg_init_kernel(const VecArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32 * 2];
   const bool guess = a.red.S->use_guess != 0;
   double v[2] = {0.0, 0.0};
@@ -902,6 +924,8 @@ __global__ void __launch_bounds__(kVecThreads) bicg_init_kernel(const VecArgs a)
 
 // BiCGSTAB restart (:75-77): r = b - A x (t holds A x), r0 = r, ||r||^2
 __global__ void __launch_bounds__(kVecThreads) bicg_restart_kernel(const VecArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32];
   if (gated_out(a.red.S, a.red.gate)) return;
   double v[1] = {0.0};
@@ -922,6 +946,8 @@ __global__ void __launch_bounds__(kVecThreads) bicg_restart_kernel(const VecArgs
 
 // BiCGSTAB :82-85: beta = (rho/rho_old)(alpha/w); p = r + beta (p - w v); y = D^-1 p
 __global__ void __launch_bounds__(kVecThreads) bicg_p_kernel(const VecArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (gated_out(a.red.S, a.red.gate)) return;
   const Scalars* S = a.red.S;
   const double beta = (S->rho / S->rho_old) * (S->alpha / S->w);
@@ -942,6 +968,8 @@ __global__ void __launch_bounds__(kVecThreads) bicg_p_kernel(const VecArgs a) {
 
 // BiCGSTAB :90-92: s = r - alpha v; z = D^-1 s
 __global__ void __launch_bounds__(kVecThreads) bicg_s_kernel(const VecArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (gated_out(a.red.S, a.red.gate)) return;
   const double alpha = a.red.S->alpha;
   vec_loop(a.n,
@@ -959,6 +987,8 @@ __global__ void __launch_bounds__(kVecThreads) bicg_s_kernel(const VecArgs a) {
 
 // BiCGSTAB :100-101 and the next loop head :67,:71: x += alpha y + w z; r = s - w t; ||r||^2; r0.r
 __global__ void __launch_bounds__(kVecThreads) bicg_update_kernel(const VecArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32 * 2];
   if (gated_out(a.red.S, a.red.gate)) return;
   const double alpha = a.red.S->alpha, w = a.red.S->w;
@@ -984,6 +1014,8 @@ __global__ void __launch_bounds__(kVecThreads) bicg_update_kernel(const VecArgs 
 
 // x = 0 when ||b|| == 0 (ConjugateGradient.h:48, BiCGSTAB.h:49); otherwise nothing.
 __global__ void __launch_bounds__(kVecThreads) finalize_kernel(const VecArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (!a.red.S->rhs_zero) return;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
