@@ -349,8 +349,9 @@ int enqueue_cg_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle c
     return rc;
   VecArgs u = make_vec(h, kEpiCgUpdate, kGateLoop, set_cond, cond);
   LAUNCH_VEC(cg_update_kernel, u);
-  VecArgs d = make_vec(h, kEpiNone, kGateLoop, false, 0);
-  LAUNCH_VEC(cg_direction_kernel, d);
+  VecArgs d = make_vec(h, kEpiNone, kGateNone, false, 0);
+  CK(launch_k(h, cg_direction_kernel, h->vec_grid, kVecThreads, 0, d, h->gridbar.as<unsigned>() + 64));
+  h->last_launches++;
   return 0;
 }
 

@@ -31,6 +31,7 @@ struct Scalars {
   int numerical_issue;
   // CG
   double rz, abs_new, abs_old, pAp, alpha, beta;
+  long long n_update, n_xapplied;  // deferred x += alpha p bookkeeping (see cg_direction_kernel)
   // BiCGSTAB
   double rho, rho_old, w, r0_sqnorm, r0v, ts, tt, rho_next, eps2;
   long long restarts;
