@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libb200sparse.so")
+# B200S_LIB lets an experiment load an alternatively built library (e.g. another CTA size); default is the in-tree build
+LIB_PATH = os.environ.get("B200S_LIB") or os.path.join(HERE, "lib", "libb200sparse.so")
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 

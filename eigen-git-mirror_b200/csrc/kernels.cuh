@@ -1135,7 +1135,7 @@ __device__ __forceinline__ void grid_sync(const RedCtx& ctx, double* v, double* 
   ++gen;
 }
 
-__global__ void __launch_bounds__(kSpmvThreads, 4) cg_persistent_kernel(const CgPersistArgs a) {
+__global__ void __launch_bounds__(kSpmvThreads, 1024 / kSpmvThreads) cg_persistent_kernel(const CgPersistArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_bar[8];
   __shared__ double red_scratch[32 * 2];

@@ -2,6 +2,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace b200s {
@@ -127,14 +128,20 @@ static void build_tiles(Plan& p, const std::vector<uint8_t>& row_is_boundary) {
       }
       int nrows = static_cast<int>(r - start);
       int mean = nrows ? (nnz + nrows - 1) / nrows : 0;
-      // lanes per row: as many as keep every row of the tile busy in one sweep of the CTA, but no more than
-      // half the mean row length (short rows are cheapest with one thread each).
+      // lanes per row: as many as keep every row of the tile busy in one sweep of the CTA, but no more than half
+      // the row length that matters -- the mean, or a quarter of the longest row when the tile is imbalanced
+      // (short rows are cheapest with one thread each; a long row among short ones needs lanes to keep the sweep
+      // from waiting on it).
+      static const int stream_factor = [] { const char* e = std::getenv("B200S_STREAM_FACTOR"); return e ? std::atoi(e) : 0; }();
+      int eff = std::max(mean, maxlen / 4);
       int lg_fit = std::min(5, floor_log2(std::max(1, kSpmvThreads / std::max(1, nrows))));
-      int lg_len = std::min(5, ceil_log2(std::max(1, mean / 2)));
+      int lg_len = std::min(5, ceil_log2(std::max(1, eff / 2)));
       int lg = std::min(lg_fit, lg_len);
       int flags = is_b ? kTileBoundary : 0;
-      // strongly imbalanced tile: balance the products over all threads first (two-phase, CSR-stream style)
-      if (maxlen > 4 * mean + 32) {
+      // Two-phase (CSR-stream) tiles: products balanced over all threads first.  Measured slower than row lanes on
+      // every matrix of the sweep (27-point: 0.53 vs 0.81 of the copy bandwidth), so it is off unless
+      // B200S_STREAM_FACTOR=f asks for it on tiles with maxlen > f*mean + 32.
+      if (stream_factor > 0 && maxlen > stream_factor * mean + 32) {
         flags |= kTileStream;
         lg = lg_fit;
         p.n_stream++;

@@ -16,9 +16,12 @@
 
 namespace b200s {
 
-constexpr int kSpmvThreads = 256;       // CTA size of the staged SpMV kernel
-constexpr int kDefaultTileNnz = 2048;   // shared-memory tile: non-zeros
-constexpr int kDefaultTileRows = 256;   // shared-memory tile: rows
+#ifndef B200S_SPMV_THREADS
+#define B200S_SPMV_THREADS 256
+#endif
+constexpr int kSpmvThreads = B200S_SPMV_THREADS;      // CTA size of the staged SpMV kernel
+constexpr int kDefaultTileNnz = 8 * kSpmvThreads;     // shared-memory tile: non-zeros
+constexpr int kDefaultTileRows = kSpmvThreads;        // shared-memory tile: rows (one thread per row at 1 lane/row)
 
 // One unit of work of the staged SpMV kernel: a run of consecutive rows whose non-zeros fit one smem stage.
 struct Tile {
