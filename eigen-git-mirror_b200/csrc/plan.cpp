@@ -132,15 +132,16 @@ static void build_tiles(Plan& p, const std::vector<uint8_t>& row_is_boundary) {
       // the row length that matters -- the mean, or a quarter of the longest row when the tile is imbalanced
       // (short rows are cheapest with one thread each; a long row among short ones needs lanes to keep the sweep
       // from waiting on it).
-      static const int stream_factor = [] { const char* e = std::getenv("B200S_STREAM_FACTOR"); return e ? std::atoi(e) : 0; }();
+      static const int stream_factor = [] { const char* e = std::getenv("B200S_STREAM_FACTOR"); return e ? std::atoi(e) : 4; }();
       int eff = std::max(mean, maxlen / 4);
       int lg_fit = std::min(5, floor_log2(std::max(1, kSpmvThreads / std::max(1, nrows))));
       int lg_len = std::min(5, ceil_log2(std::max(1, eff / 2)));
       int lg = std::min(lg_fit, lg_len);
       int flags = is_b ? kTileBoundary : 0;
-      // Two-phase (CSR-stream) tiles: products balanced over all threads first.  Measured slower than row lanes on
-      // every matrix of the sweep (27-point: 0.53 vs 0.81 of the copy bandwidth), so it is off unless
-      // B200S_STREAM_FACTOR=f asks for it on tiles with maxlen > f*mean + 32.
+      // Two-phase (CSR-stream) tiles: products balanced over all threads first, then summed per row.  Measured
+      // (profiles/r1_spmv_sweep.jsonl and the round-1 experiments in DESIGN.md): on balanced tiles it loses to row
+      // lanes (27-point 0.53 vs 0.81 of the copy bandwidth, so it is never forced there), on strongly imbalanced
+      // tiles (power-law rows, maxlen > 4*mean + 32) it wins by 10-45 %.  B200S_STREAM_FACTOR changes the 4; 0 = off.
       if (stream_factor > 0 && maxlen > stream_factor * mean + 32) {
         flags |= kTileStream;
         lg = lg_fit;
