@@ -318,7 +318,7 @@ def run_ours(args):
                        "parallelism": f"row-block x{world}" if world > 1 else "single GPU",
                        "l2": "working set per iteration (3.2 GB at 256^3) exceeds L2; no explicit flush",
                        "iterations_per_solve": iters, "error": err, "info": info, "true_residual": true_res,
-                       "loop_mode": stats["loop_mode"], "spmv_grid": stats["spmv_grid"],
+                       "loop_mode": stats["loop_mode"], "evict_first": stats["evict_first"], "spmv_grid": stats["spmv_grid"],
                        "spmv_stages": stats["spmv_stages"], "setup_s": round(t_setup, 2)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rows * 8) * world,
                     "d2h_bytes_per_step": int(rows * 8) * world, "ms_per_step": 1e3 * e2e_s / args.steps},

@@ -26,7 +26,8 @@ class Stats(C.Structure):
         ("tiles", C.c_int32), ("tiles_boundary", C.c_int32), ("tiles_by_lanes", C.c_int32 * 6),
         ("tiles_stream", C.c_int32), ("tiles_long", C.c_int32),
         ("spmv_grid", C.c_int32), ("spmv_block", C.c_int32), ("spmv_smem_bytes", C.c_int32), ("spmv_stages", C.c_int32),
-        ("vec_grid", C.c_int32), ("vec_block", C.c_int32), ("loop_mode", C.c_int32), ("sm_count", C.c_int32),
+        ("vec_grid", C.c_int32), ("vec_block", C.c_int32), ("loop_mode", C.c_int32), ("evict_first", C.c_int32),
+        ("sm_count", C.c_int32),
         ("last_solve_ms", C.c_double), ("last_h2d_ms", C.c_double), ("last_d2h_ms", C.c_double),
         ("last_kernel_launches", C.c_int64), ("last_iterations", C.c_int64), ("last_spmv_count", C.c_int64),
         ("device_bytes", C.c_int64),

@@ -91,6 +91,7 @@ typedef struct {
   int32_t spmv_grid, spmv_block, spmv_smem_bytes, spmv_stages;
   int32_t vec_grid, vec_block;
   int32_t loop_mode;                /* resolved */
+  int32_t evict_first;              /* matrix stream uses the L2 evict-first policy (auto: vectors fit L2, matrix does not) */
   int32_t sm_count;
   double last_solve_ms;             /* device time of the last solve (CUDA events around the graph launch) */
   double last_h2d_ms, last_d2h_ms;  /* host<->device copies of the last host-buffer call */
