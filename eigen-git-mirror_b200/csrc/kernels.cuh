@@ -920,6 +920,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgs
     if (t == gridDim.x - 1) {  // every CTA has read the counters long ago: safe to retire the pending update
       *ticket = 0;
       a.red.S->n_xapplied = S->n_update;
+      timeline_mark(a.red.S, 10);  // interval "update epilogue -> end of the direction pass"
     }
   }
 }

@@ -342,7 +342,7 @@ class _IterativeSolverBase(SparseOperator):
         out = np.zeros(27)
         self._hd.check(self._hd.L.b200s_get_timeline(self._hd.h, _ptr(out), 27))
         names = {1: "spmv_only", 2: "cg_init", 3: "spmv_pAp", 4: "cg_update", 5: "bicg_init", 6: "spmv_r0v",
-                 7: "spmv_ts_tt", 8: "bicg_update", 9: "bicg_restart"}
+                 7: "spmv_ts_tt", 8: "bicg_update", 9: "bicg_restart", 10: "cg_direction"}
         d = {f"{names[e]}_us_avg": out[e] / out[12 + e] for e in names if out[12 + e] > 0}
         d.update(allreduce_us_total=out[24], halo_wait_us_total=out[25], span_us=out[26],
                  reductions=int(out[12:24].sum()))

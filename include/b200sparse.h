@@ -161,7 +161,7 @@ int64_t b200s_get_residual_history(b200s_handle* h, double* rr, int64_t cap);
 
 /* Device-side timeline of the last solve (globaltimer, this rank): out[e] / out[12+e] = microseconds / count of the
  * interval ending at reduction kind e (1 spmv-only, 2 cg-init, 3 p.Ap, 4 cg-update, 5 bicg-init, 6 r0.v, 7 t.s/t.t,
- * 8 bicg-update, 9 restart), each including the launch gap before it; out[24] = time inside cross-rank all-reduces,
+ * 8 bicg-update, 9 restart, 10 end of the CG direction pass), each including the launch gap before it; out[24] = time inside cross-rank all-reduces,
  * out[25] = time CTA 0 waited for halo entries, out[26] = first-to-last reduction.  cap >= 27. */
 int b200s_get_timeline(b200s_handle* h, double* out, int cap);
 
