@@ -884,7 +884,11 @@ int b200s_create(const b200s_config* cfg, b200s_handle** out) {
     return B200S_ERR_CUDA;
   }
   std::memset(h->hS, 0, sizeof(Scalars));
-  h->loop_mode = h->cfg.loop_mode ? h->cfg.loop_mode : env_int("B200S_LOOP_MODE", B200S_LOOP_WHILE_GRAPH);
+  // AUTO: one GPU -> WHILE graph; row-partitioned runs -> persistent cooperative kernel for CG (BiCGSTAB keeps the
+  // WHILE graph).  Measured on 8xB200 with identical results: 512^3 582 -> 539 us per iteration, 256^3 88.4 -> 87.2;
+  // on one GPU the two are within 2 % of each other (profiles/r1_loop_overheads.txt).
+  h->loop_mode = h->cfg.loop_mode ? h->cfg.loop_mode : env_int("B200S_LOOP_MODE", B200S_LOOP_AUTO);
+  if (h->loop_mode == B200S_LOOP_AUTO) h->loop_mode = (h->cfg.world > 1) ? B200S_LOOP_PERSISTENT : B200S_LOOP_WHILE_GRAPH;
   h->spmv_impl = h->cfg.spmv_impl ? h->cfg.spmv_impl : env_int("B200S_SPMV_IMPL", B200S_SPMV_STAGED);
   h->evict_first = env_int("B200S_EVICT_FIRST", -1);  // -1: decided per problem in configure_spmv
   // measured (profiles/r1_loop_overheads.txt): PDL with an early trigger lets dependent CTAs squat on registers and
