@@ -53,7 +53,8 @@ struct b200s_handle {
   bool analyzed = false, factorized = false;
   int scalar_bytes = 0;  // 8 = f64, 4 = f32
   int precond = B200S_PRECOND_JACOBI;
-  int loop_mode = B200S_LOOP_WHILE_GRAPH;
+  int loop_mode = B200S_LOOP_WHILE_GRAPH;  // resolved per problem in analyze_pattern when AUTO was requested
+  bool loop_auto = false;
   int spmv_impl = B200S_SPMV_STAGED;
   int direct_lg = 0;
   // device pattern / values
@@ -811,6 +812,8 @@ int configure_spmv(b200s_handle* h) {
     else
       h->evict_first = (l2 > 0 && vec_bytes <= 1.75 * l2 && !all_fits) ? 1 : 0;
   }
+  if (h->loop_auto)
+    h->loop_mode = (p.world > 1 || p.rows >= (int64_t(1) << 22)) ? B200S_LOOP_PERSISTENT : B200S_LOOP_WHILE_GRAPH;
   // direct kernel: lanes per row from the global mean row length
   int mean = p.rows ? static_cast<int>((p.nnz + p.rows - 1) / p.rows) : 1;
   int lg = 0;
@@ -884,11 +887,13 @@ int b200s_create(const b200s_config* cfg, b200s_handle** out) {
     return B200S_ERR_CUDA;
   }
   std::memset(h->hS, 0, sizeof(Scalars));
-  // AUTO: one GPU -> WHILE graph; row-partitioned runs -> persistent cooperative kernel for CG (BiCGSTAB keeps the
-  // WHILE graph).  Measured on 8xB200 with identical results: 512^3 582 -> 539 us per iteration, 256^3 88.4 -> 87.2;
-  // on one GPU the two are within 2 % of each other (profiles/r1_loop_overheads.txt).
+  // AUTO: the persistent cooperative kernel drives CG in row-partitioned runs and on one GPU for large problems
+  // (>= 4M rows per GPU); small single-GPU problems and BiCGSTAB use the WHILE graph.  Measured with identical
+  // results (profiles/r1_loop_overheads.txt): 8xB200 512^3 582 -> 539 us per iteration, 256^3 88.4 -> 87.2;
+  // one GPU 256^3 544 -> 524; one GPU 128^3 82.9 (WHILE) vs 86.4.
   h->loop_mode = h->cfg.loop_mode ? h->cfg.loop_mode : env_int("B200S_LOOP_MODE", B200S_LOOP_AUTO);
-  if (h->loop_mode == B200S_LOOP_AUTO) h->loop_mode = (h->cfg.world > 1) ? B200S_LOOP_PERSISTENT : B200S_LOOP_WHILE_GRAPH;
+  h->loop_auto = (h->loop_mode == B200S_LOOP_AUTO);
+  if (h->loop_auto) h->loop_mode = (h->cfg.world > 1) ? B200S_LOOP_PERSISTENT : B200S_LOOP_WHILE_GRAPH;
   h->spmv_impl = h->cfg.spmv_impl ? h->cfg.spmv_impl : env_int("B200S_SPMV_IMPL", B200S_SPMV_STAGED);
   h->evict_first = env_int("B200S_EVICT_FIRST", -1);  // -1: decided per problem in configure_spmv
   // measured (profiles/r1_loop_overheads.txt): PDL with an early trigger lets dependent CTAs squat on registers and
