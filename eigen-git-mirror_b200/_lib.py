@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
     L.b200s_plan_probe.argtypes = [C.POINTER(Config), i64, i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp,
                                    C.POINTER(Stats)]
     L.b200s_plan_probe.restype = i64
+    L.b200s_plan_probe_csr.argtypes = [i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64]
+    L.b200s_plan_probe_csr.restype = i64
     _lib = L
     return L
 

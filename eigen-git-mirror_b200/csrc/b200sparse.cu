@@ -1139,4 +1139,25 @@ int64_t b200s_plan_probe(const b200s_config* cfg, int64_t rows, int64_t cols, in
   return static_cast<int64_t>(p.ghost_cols.size());
 }
 
+int64_t b200s_plan_probe_csr(int64_t rows, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                             const int32_t* inner_nnz, int uplo, int32_t* out_rowptr, int32_t* out_colidx,
+                             int32_t* out_src, int64_t cap) {
+  b200s_config c;
+  std::memset(&c, 0, sizeof(c));
+  c.world = 1;
+  Plan p;
+  std::string err;
+  int rc = build_plan(c, rows, rows, nnz, rowptr, colidx, inner_nnz, uplo, nullptr, p, err);
+  if (rc) {
+    g_create_error = err;
+    return rc;
+  }
+  if (out_rowptr) std::memcpy(out_rowptr, p.rowptr.data(), sizeof(int32_t) * static_cast<size_t>(rows + 1));
+  const int64_t n = std::min<int64_t>(cap, p.nnz);
+  if (out_colidx && n > 0) std::memcpy(out_colidx, p.colidx_ptr(), sizeof(int32_t) * static_cast<size_t>(n));
+  if (out_src)
+    for (int64_t k = 0; k < n; ++k) out_src[k] = p.src.empty() ? static_cast<int32_t>(k) : p.src[k];
+  return p.nnz;
+}
+
 }  // extern "C"

@@ -55,3 +55,21 @@ def probe(A, comm: Optional[Communicator] = None, tile_nnz: int = 0, tile_rows: 
             msg += f" ({comm.errors[-1]!r})"
         raise _lib.B200Error(int(n), msg)
     return PlanView(ghosts[:n].copy(), local, send_rows[:int(sc.sum())].copy(), sc, rc, st.as_dict())
+
+
+def canonical_csr(A, uplo: int = 3, inner_nnz=None):
+    """The single-rank device matrix analyze_pattern builds from an uncompressed and / or one-triangle input:
+    returns (rowptr, colidx, src) with src[k] = index into A.vals that entry k copies (GPU-free)."""
+    A = _as_csr(A)
+    L = _lib.lib()
+    inz = None if inner_nnz is None else np.ascontiguousarray(inner_nnz, np.int32)
+    nnz_in = int(A.colidx.shape[0])
+    cap = 2 * nnz_in + 1
+    rowptr = np.zeros(A.rows + 1, np.int32)
+    colidx = np.zeros(cap, np.int32)
+    src = np.zeros(cap, np.int32)
+    n = L.b200s_plan_probe_csr(A.rows, nnz_in, _ptr(A.rowptr), _ptr(A.colidx), _ptr(inz), uplo, _ptr(rowptr),
+                               _ptr(colidx), _ptr(src), cap)
+    if n < 0:
+        raise _lib.B200Error(int(n), L.b200s_last_error(None).decode())
+    return rowptr, colidx[:n].copy(), src[:n].copy()

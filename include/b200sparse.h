@@ -176,6 +176,15 @@ int64_t b200s_plan_probe(const b200s_config* cfg, int64_t rows, int64_t cols, in
                          int64_t* ghost_cols, int64_t ghost_cap, int32_t* send_rows, int64_t send_cap,
                          int64_t* send_counts, int64_t* recv_counts, b200s_stats* tile_stats);
 
+/* GPU-free view of the canonical device matrix analyze_pattern would build on ONE rank from an uncompressed and/or
+ * one-triangle input: compressed CSR, symmetric expansion for LOWER / UPPER (what selfadjointView implies,
+ * SparseSelfAdjointView.h:279-337).  out_rowptr has rows+1 entries; out_colidx / out_src (optional) receive up to `cap`
+ * entries, out_src[k] being the index into the caller's value array that entry k takes its value from.  Returns the
+ * number of entries of the canonical matrix, or a negative status. */
+int64_t b200s_plan_probe_csr(int64_t rows, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                             const int32_t* inner_nnz, int uplo, int32_t* out_rowptr, int32_t* out_colidx,
+                             int32_t* out_src, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

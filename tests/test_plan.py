@@ -66,3 +66,57 @@ def test_invalid_inputs_are_rejected():
     rect = wl.CsrMatrix(3, 4, np.array([0, 1, 2, 3], np.int32), np.array([0, 1, 3], np.int32), np.ones(3))
     with pytest.raises(egm.B200Error):
         planning.probe(rect)
+
+
+def _dense_from(rowptr, colidx, vals, n):
+    import scipy.sparse as sp
+    return sp.csr_matrix((vals, colidx, rowptr), shape=(n, n)).toarray()
+
+
+@pytest.mark.parametrize("uplo", [1, 2])
+def test_one_triangle_is_expanded_to_the_full_symmetric_matrix(uplo):
+    """UpLo = Lower / Upper (ConjugateGradient.h:202-213): the device matrix is what selfadjointView<UpLo> denotes,
+    whether the input stores only that triangle or the whole matrix (the other triangle is then ignored)."""
+    import scipy.sparse as sp
+    A = wl.varcoef3d(5)
+    S = A.to_scipy()
+    full = S.toarray()
+    half = sp.tril(S) if uplo == 1 else sp.triu(S)
+    junk = S.copy().tolil()
+    junk_dense = full.copy()
+    if uplo == 1:   # poison the triangle that must not be read
+        junk_dense[np.triu_indices(A.rows, 1)] *= 7.0
+    else:
+        junk_dense[np.tril_indices(A.rows, -1)] *= 7.0
+    J = sp.csr_matrix(junk_dense)
+    for M in (half.tocsr(), J):
+        M.sort_indices()
+        In = wl.CsrMatrix(A.rows, A.rows, M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.copy())
+        rowptr, colidx, src = planning.canonical_csr(In, uplo=uplo)
+        got = _dense_from(rowptr, colidx, In.vals[src], A.rows)
+        assert np.array_equal(got, full)
+        for i in range(A.rows):  # rows stay sorted when the input rows are sorted
+            assert np.all(np.diff(colidx[rowptr[i]:rowptr[i + 1]]) > 0)
+
+
+def test_uncompressed_input_is_compressed():
+    """innerNonZeroPtr semantics (SparseMatrix.h:176-183): only the first inner_nnz[i] slots of each row count."""
+    A = wl.powerlaw(300, 6, seed=2)
+    lens = np.diff(A.rowptr)
+    pad = np.arange(A.rows) % 4
+    rowptr = np.zeros(A.rows + 1, np.int32)
+    rowptr[1:] = np.cumsum(lens + pad)
+    colidx = np.full(rowptr[-1], 0, np.int32)
+    vals = np.full(rowptr[-1], np.nan)
+    for i in range(A.rows):
+        colidx[rowptr[i]:rowptr[i] + lens[i]] = A.colidx[A.rowptr[i]:A.rowptr[i + 1]]
+        vals[rowptr[i]:rowptr[i] + lens[i]] = A.vals[A.rowptr[i]:A.rowptr[i + 1]]
+    U = wl.CsrMatrix(A.rows, A.cols, rowptr, colidx, vals)
+    rp, ci, src = planning.canonical_csr(U, inner_nnz=lens.astype(np.int32))
+    assert np.array_equal(rp, A.rowptr) and np.array_equal(ci, A.colidx) and np.array_equal(vals[src], A.vals)
+
+
+def test_compressed_full_input_is_passed_through():
+    A = wl.poisson2d(9)
+    rp, ci, src = planning.canonical_csr(A)
+    assert np.array_equal(rp, A.rowptr) and np.array_equal(ci, A.colidx) and np.array_equal(src, np.arange(A.nnz))
