@@ -1,4 +1,4 @@
-"""GPU: API conformance through the C++ binding.  oracle/_ref/conformance_{cg,bicgstab} are the reference's own test
+"""GPU: API conformance through the C++ binding.  oracle/_ref/conformance_b200 holds the reference's own test
 drivers (test/sparse_solver.h: check_sparse_spd_solving / check_sparse_square_solving -- dense, sparse and
 multi-column right-hand sides, solveWithGuess, analyzePattern+factorize, Map / uncompressed / expression inputs,
 matrix constructor, results against dense Householder QR at 1e-6) instantiated on b200::ConjugateGradient and
@@ -13,10 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
-@pytest.mark.parametrize("name", ["conformance_cg", "conformance_bicgstab"])
 @pytest.mark.parametrize("seed", [42, 20261017])
-def test_reference_driver_on_b200_solvers(name, seed, egm):
-    exe = os.path.join(ROOT, "oracle", "_ref", name)
+def test_reference_driver_on_b200_solvers(seed, egm):
+    exe = os.path.join(ROOT, "oracle", "_ref", "conformance_b200")
     if not os.path.exists(exe):
         pytest.skip(f"{exe} not built (needs /root/reference: make -C oracle conformance)")
     res = subprocess.run([exe, f"s{seed}", "r3"], capture_output=True, text=True, timeout=800)
