@@ -262,7 +262,10 @@ void NAME(oracle_bicgstab)(int64_t n, const int32_t* rowptr, const int32_t* coli
         w = NAME(oracle_dot)(t, s, n, lanes) / tt; /* :96-97 */
       else
         w = (REAL)0;
-      for (int64_t i = 0; i < n; ++i) x[i] = x[i] + FMA(w, z[i], alpha * y[i]); /* :100 */
+      /* :100 x += alpha*y + w*z: GCC fuses w*z into the inner add.  (Pinned bit-for-bit on the AVX-512 build of
+       * oracle/_ref; the AVX2 build contracts the scalar remainder of this one statement differently, so on vectors
+       * whose length is not a multiple of 4 its x differs from this port in the last bit.) */
+      for (int64_t i = 0; i < n; ++i) x[i] = x[i] + FMA(w, z[i], alpha * y[i]);
       for (int64_t i = 0; i < n; ++i) r[i] = FMA(-w, t[i], s[i]);               /* :101 */
       ++i_it;
       rr = NAME(oracle_dot)(r, r, n, lanes);

@@ -72,3 +72,31 @@ def test_reference_semantics_visible_in_goldens(golden, variant):
     assert g("cg/poisson3d_10/guess_exact", "iters") == 0
     # maxIterations = k stops after exactly k iterations with NoConvergence
     assert g("cg/poisson3d_10/traj_k5", "iters") == 5 and g("cg/poisson3d_10/traj_k5", "info") == 2
+
+
+@pytest.mark.parametrize("forced", ["v3", "v4"])
+def test_both_isa_variants_are_reproduced(forced, golden, port):
+    """Whatever CPU this runs on, the port reproduces BOTH reference builds when told their packet width: 4 doubles /
+    float body of 4 for x86-64-v3, 8 doubles / float body of 8 for x86-64-v4."""
+    lanes = 4 if forced == "v3" else 8
+    for case in ("cg/varcoef3d_10/uplo3_pre1", "cg/random_spd_80/ones", "cg/poisson2d_24/guess"):
+        A = golden.matrix(case)
+        x0 = golden.get(case, "x0") if int(golden.get(case, "has_guess")) else None
+        x, it, err, info = port.cg(A, golden.get(case, "b"), x0=x0, tol=float(golden.get(case, "tol")),
+                                   max_iters=int(golden.get(case, "max_iters")), uplo=int(golden.get(case, "uplo")),
+                                   precond=int(golden.get(case, "precond")), lanes=lanes)
+        assert it == int(golden.get(case, f"iters_{forced}")) and err == float(golden.get(case, f"error_{forced}"))
+        assert np.array_equal(x, golden.get(case, f"x_{forced}"))
+    # BiCGSTAB: pinned on the AVX-512 build; the AVX2 build contracts the scalar remainder of `x += alpha*y + w*z`
+    # differently, which shows on vector lengths that are not a multiple of 4 (random_square_90), not on 512 = 8^3
+    for case in (("bicgstab/random_square_90/pre0", "bicgstab/varcoef3d_8/pre1") if forced == "v4"
+                 else ("bicgstab/varcoef3d_8/pre1",)):
+        A = golden.matrix(case)
+        x, it, err, info = port.bicgstab(A, golden.get(case, "b"), tol=float(golden.get(case, "tol")),
+                                         max_iters=int(golden.get(case, "max_iters")),
+                                         precond=int(golden.get(case, "precond")), lanes=lanes)
+        assert it == int(golden.get(case, f"iters_{forced}")) and np.array_equal(x, golden.get(case, f"x_{forced}"))
+    case = "spmv/banded_500_k16/f32"
+    A = golden.matrix(case)
+    y = port.spmv(A, golden.get(case, "x"), blk=4 if forced == "v3" else 8)
+    assert np.array_equal(y, golden.get(case, f"y_{forced}"))
