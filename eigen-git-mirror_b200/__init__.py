@@ -6,6 +6,7 @@ Layout
   solvers.py    host-side mirror of Eigen's solver interface over that C ABI (ctypes)
   planning.py   GPU-free view of the partition / halo / tile plan (host logic, testable on CPU)
   workloads.py  synthetic CSR matrices of BASELINE.json
+  marketio.py   MatrixMarket I/O with the reference's semantics (SparseExtra/MarketIO.h), host-side
   build.py      nvcc build (in-tree)
 
 Importing the package does not load the CUDA library; the first solver / operator does, and raises if it is missing.
