@@ -12,8 +12,13 @@ A "step" is one full CG solve.  `value` = CG iterations per second with b and x 
 events on the library's stream around the graph launch, max over ranks); `e2e` = the same metric through the public
 host API (pinned host buffers; H2D of b and D2H of x inside the timed region, wall clock).  `roofline` describes the
 dominant kernel (the SpMV fused with p.Ap), timed alone with CUDA events on its launching stream.  `cpu_baseline` is
-the unmodified reference (Eigen, oracle/_ref) on the host cores for a bounded number of iterations of the same solve.
+the unmodified reference (Eigen, oracle/_ref) on the host cores for a bounded number of iterations of the same solve;
+its x after those iterations is compared with the GPU's x at the same maxIterations (`config.parity_k_rel`).
 `--impl reference` runs only that CPU arm.  Nothing here reads /root/reference at run time.
+
+The headline line also carries `configs`: the other BASELINE.json configurations measured in the same run with the same
+protocol (extra keys; the headline keys are unchanged) -- at N=1 configs[2] (BiCGSTAB 256^3), configs[0] (2D 1024^2) and
+configs[3] (the SpMV sweep, see --sweep-rows); at N=8 configs[4] (512^3 CG).  --no-extras skips them.
 """
 from __future__ import annotations
 
@@ -61,6 +66,14 @@ def iteration_bytes(nnz, rows, solver):
     """Algorithmic bytes per iteration: CG 12 nnz + 4(N+1) + 13*8 N; BiCGSTAB 2(...) + 25*8 N."""
     m = 12 * nnz + 4 * (rows + 1)
     return m + 104 * rows if solver == "cg" else 2 * m + 200 * rows
+
+
+def host_threads():
+    """Cores this process may run on -- not OMP_NUM_THREADS, which torch.distributed.run pins to 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -112,16 +125,16 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(n, solver, iters_cap, threads=None):
-    """The unmodified reference on the host cores: one CG/BiCGSTAB run capped at `iters_cap` iterations."""
+def cpu_reference_problem(n, solver):
+    """Inputs of the reference arm: the whole matrix and b = A x_true, as tests and the GPU arm build them."""
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())  # before libgomp loads with the checker
     from oracle import loader
     from eigen_git_mirror_b200 import workloads as wl
     R = loader.ref()
-    threads = threads or R.max_threads
     A = build_block(n, solver, 0, n ** 3)
     x_true = wl.random_vector(A.rows, 12345)
     b = wl.rhs_from_solution(A, x_true)
-    return R, A, b, threads
+    return R, A, b, host_threads()
 
 
 def run_reference(args):
@@ -132,7 +145,7 @@ def run_reference(args):
     n, solver = args.grid, args.solver
     # bounded sample: m iterations per step so that the run ends within minutes (256^3: ~0.2 s/iteration on 8 threads)
     m = args.ref_iters or max(2, int(round(20 * (256 / n) ** 3)))
-    R, A, b, threads = cpu_reference_run(n, solver, m)
+    R, A, b, threads = cpu_reference_problem(n, solver)
     fn = R.cg if solver == "cg" else R.bicgstab
     for _ in range(args.warmup):
         fn(A, b, tol=TOL, max_iters=min(m, 2), threads=threads)
@@ -157,86 +170,191 @@ def run_reference(args):
     return 0
 
 
-def run_ours(args):
-    import torch
-    import eigen_git_mirror_b200 as egm
-    from eigen_git_mirror_b200 import workloads as wl
+class Env:
+    """Process-group plumbing of one bench process (one per GPU)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one process per GPU)")
-    torch.cuda.set_device(local_rank)
-    if egm.device_count() < 1:
-        raise SystemExit("no sm_100 device: the product has no CPU fallback")
-    comm, gloo = None, None
-    n, solver = args.grid, args.solver
-    N = n ** 3
-    if world > 1:
-        import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-        gloo = dist.new_group(backend="gloo")
-        starts = egm.partition_rows(N, world, align=n * n)  # k-slabs: one n^2 plane of halo per neighbour
-        comm = egm.Communicator.from_torch(starts, group=gloo)
-        r0, r1 = int(starts[rank]), int(starts[rank + 1])
-    else:
-        r0, r1 = 0, N
-
-    t_setup = time.perf_counter()
-    A = build_block(n, solver, r0, r1)
-    x_true = wl.random_vector(N, 12345)
-    b_host = np.asarray(A.to_scipy() @ x_true)           # this rank's block of b = A x_true (setup, untimed)
-    nnz_global, rows_global = (7 * N - 6 * n * n), N
-    Solver = egm.ConjugateGradient if solver == "cg" else egm.BiCGSTAB
-    s = Solver(comm=comm, device=local_rank)
-    s.compute(A)
-    s.setTolerance(TOL)
-    t_setup = time.perf_counter() - t_setup
-    stats = s.stats()
-
-    rows = A.rows
-    b_pin = torch.empty(rows, dtype=torch.float64).pin_memory()
-    b_pin.numpy()[:] = b_host
-    x_pin = torch.empty(rows, dtype=torch.float64).pin_memory()
-    b_dev = b_pin.cuda(non_blocking=False)
-    x_dev = torch.zeros(rows, dtype=torch.float64, device="cuda")
-
-    def barrier():
-        if world > 1:
+        torch.cuda.set_device(self.local_rank)
+        self.dist, self.gloo = None, None
+        if self.world > 1:
             import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
+            self.gloo = dist.new_group(backend="gloo")
+            self.dist = dist
 
-    def max_over_ranks(v):
-        if world == 1:
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if not self.dist:
             return v
-        import torch.distributed as dist
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident arm: `value` ----
-    for _ in range(args.warmup):
+    def sum_over_ranks(self, vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+
+def make_problem(env, egm, n, solver, dims=3):
+    """This rank's row block of the stencil problem, its b block and a configured solver."""
+    from eigen_git_mirror_b200 import workloads as wl
+    N = n ** dims
+    comm = None
+    if env.world > 1:
+        starts = egm.partition_rows(N, env.world, align=n ** (dims - 1))  # slabs: one plane of halo per neighbour
+        comm = egm.Communicator.from_torch(starts, group=env.gloo)
+        r0, r1 = int(starts[env.rank]), int(starts[env.rank + 1])
+    else:
+        r0, r1 = 0, N
+    t0 = time.perf_counter()
+    A = wl.poisson2d(n, rows=(r0, r1)) if dims == 2 else build_block(n, solver, r0, r1)
+    x_true = wl.random_vector(N, 12345)
+    b_host = np.asarray(A.to_scipy() @ x_true)           # this rank's block of b = A x_true (setup, untimed)
+    Solver = egm.ConjugateGradient if solver == "cg" else egm.BiCGSTAB
+    s = Solver(comm=comm, device=env.local_rank)
+    s.compute(A)
+    s.setTolerance(TOL)
+    nnz_global = (7 * N - 6 * n * n) if dims == 3 else (5 * N - 4 * n)
+    return dict(A=A, b_host=b_host, x_true=x_true, s=s, comm=comm, r0=r0, r1=r1, N=N, nnz=nnz_global,
+                setup_s=time.perf_counter() - t0)
+
+
+def time_device_solves(env, s, b_dev, x_dev, steps, warmup):
+    for _ in range(warmup):
         s.solve_device(b_dev, x_dev)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
+    env.barrier()
     dev_ms, launches, iters_total = 0.0, 0, 0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         s.solve_device(b_dev, x_dev)
         st = s.stats()
         dev_ms += st["last_solve_ms"]
         launches += st["last_kernel_launches"]
         iters_total += s.iterations()
-    barrier()
+    env.barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
+    return env.max_over_ranks(dev_ms), launches, iters_total, wall_ms
+
+
+def true_residual(env, op, b_dev, x_dev):
+    """||b - A x|| / ||b|| with the (row-partitioned) device product and norms summed over ranks."""
+    torch = env.torch
+    r_dev = torch.empty_like(x_dev)
+    op.multiply_device(x_dev, r_dev, reps=1)
+    d = b_dev - r_dev
+    num, den = env.sum_over_ranks([float(torch.dot(d, d)), float(torch.dot(b_dev, b_dev))])
+    return float(np.sqrt(num / den))
+
+
+def side_config(env, egm, n, solver, dims, steps, warmup, peak):
+    """One of the non-headline BASELINE configurations, same protocol: device-resident solves, CUDA-event time."""
+    torch = env.torch
+    P = make_problem(env, egm, n, solver, dims)
+    s, rows = P["s"], P["A"].rows
+    b_dev = torch.from_numpy(P["b_host"]).cuda()
+    x_dev = torch.zeros(rows, dtype=torch.float64, device="cuda")
+    dev_ms, launches, iters_total, _ = time_device_solves(env, s, b_dev, x_dev, steps, warmup)
+    op = egm.SparseOperator(comm=P["comm"], device=env.local_rank)
+    op.compute(P["A"])
+    res = true_residual(env, op, b_dev, x_dev)
+    it_bytes = iteration_bytes(P["nnz"], P["N"], solver)
+    gbs = it_bytes * iters_total / (dev_ms * 1e-3) / 1e9
+    out = {"workload": (workload_name(n, solver) if dims == 3 else
+                        f"2D 5-point Poisson {n}^2, ConjugateGradient<double> + DiagonalPreconditioner, tol {TOL:g}, b=A*x_true"),
+           "n_gpus": env.world, "value": iters_total / (dev_ms * 1e-3), "unit": UNIT, "steps": steps,
+           "iterations_per_solve": s.iterations(), "error": s.error(), "info": s.info(), "true_residual": res,
+           "us_per_iteration": 1e3 * dev_ms / max(1, iters_total), "iteration_bytes": it_bytes,
+           "iteration_gbs": gbs, "frac_of_hbm": gbs / (peak * env.world), "loop_mode": s.stats()["loop_mode"],
+           "gpu_launches": int(launches), "setup_s": round(P["setup_s"], 2)}
+    if solver == "bicgstab":
+        out["restarts"] = s.stats()["last_restarts"]
+    s.close()
+    op.close()
+    del b_dev, x_dev
+    torch.cuda.empty_cache()
+    return out
+
+
+def spmv_sweep(env, egm, rows, peak, reps=20):
+    """configs[3]: SpMV-only sweep on synthetic CSR, float and double, device-resident x / y, best of
+    3 runs of `reps` back-to-back products after 5 warm-ups; GB/s = algorithmic bytes / time."""
+    from eigen_git_mirror_b200 import workloads as wl
+    torch = env.torch
+    fams = [("banded_k4", lambda: wl.banded(rows, 4)), ("banded_k16", lambda: wl.banded(rows, 16)),
+            ("banded_k50", lambda: wl.banded(rows, 50)), ("banded_k100", lambda: wl.banded(rows, 100)),
+            ("stencil27_192", lambda: wl.stencil27(192)),
+            ("powerlaw_m8", lambda: wl.powerlaw(rows, 8)), ("powerlaw_m32", lambda: wl.powerlaw(rows, 32)),
+            ("powerlaw_m100", lambda: wl.powerlaw(rows, 100)), ("powerlaw_m200", lambda: wl.powerlaw(rows, 200))]
+    out = {}
+    for name, gen in fams:
+        A = gen()
+        entry = {"rows": A.rows, "nnz": A.nnz}
+        for dt, tag in ((np.float64, "f64"), (np.float32, "f32")):
+            Ad = A.astype(dt)
+            op = egm.SparseOperator(Ad, device=env.local_rank)
+            x = torch.from_numpy(wl.random_vector(A.cols, 54321, dt)).cuda()
+            y = torch.empty(A.rows, dtype=x.dtype, device="cuda")
+            op.multiply_device(x, y, reps=5)
+            ms = min(op.multiply_device(x, y, reps=reps) for _ in range(3))
+            gbs = Ad.spmv_bytes() / (ms * 1e-3) / 1e9
+            st = op.stats()
+            entry[tag] = {"ms": ms, "gbs": gbs, "frac_of_hbm": gbs / peak, "bytes": Ad.spmv_bytes(),
+                          "tiles_by_lanes": st["tiles_by_lanes"], "tiles_stream": st["tiles_stream"],
+                          "tiles_long": st["tiles_long"]}
+            op.close()
+            del x, y
+        out[name] = entry
+        del A
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import eigen_git_mirror_b200 as egm
+    from eigen_git_mirror_b200 import workloads as wl
+
+    env = Env(args)
+    torch = env.torch
+    world, rank = env.world, env.rank
+    if egm.device_count() < 1:
+        raise SystemExit("no sm_100 device: the product has no CPU fallback")
+    n, solver = args.grid, args.solver
+    peak, peak_src = measured_peak_gbs()
+
+    P = make_problem(env, egm, n, solver)
+    A, s, comm, r0, r1, N = P["A"], P["s"], P["comm"], P["r0"], P["r1"], P["N"]
+    nnz_global, rows_global, x_true, setup_s = P["nnz"], N, P["x_true"], P["setup_s"]
+    stats = s.stats()
+    rows = A.rows
+    b_pin = torch.empty(rows, dtype=torch.float64).pin_memory()
+    b_pin.numpy()[:] = P["b_host"]
+    x_pin = torch.empty(rows, dtype=torch.float64).pin_memory()
+    b_dev = b_pin.cuda(non_blocking=False)
+    x_dev = torch.zeros(rows, dtype=torch.float64, device="cuda")
+
+    # ---- device-resident arm: `value` ----
+    for _ in range(args.warmup):
+        s.solve_device(b_dev, x_dev)
+    sampler = ClockSampler(env.local_rank)
+    env.barrier()
+    sampler.start()
+    dev_ms, launches, iters_total, wall_ms = time_device_solves(env, s, b_dev, x_dev, args.steps, 0)
     clocks = sampler.stop()
-    dev_ms = max_over_ranks(dev_ms)
     iters = s.iterations()
     err, info = s.error(), s.info()
     value = iters_total / (dev_ms * 1e-3)
@@ -259,26 +377,24 @@ def run_ours(args):
 
     for _ in range(min(args.warmup, 2)):
         host_solve()
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     e2e_iters = 0
     for _ in range(args.steps):
         e2e_iters += host_solve()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    env.barrier()
+    e2e_s = env.max_over_ranks(time.perf_counter() - t0)
     e2e_value = e2e_iters / e2e_s
-    true_res = None
 
     # ---- dominant kernel alone: SpMV (+ fused dot in the solver), CUDA events on the library stream ----
-    op = egm.SparseOperator(comm=comm, device=local_rank)
+    op = egm.SparseOperator(comm=comm, device=env.local_rank)
     op.compute(A)
-    xv = torch.from_numpy(x_true[r0:r1].copy()).cuda() if world > 1 else torch.from_numpy(x_true).cuda()
+    xv = torch.from_numpy(x_true[r0:r1].copy()).cuda()
     yv = torch.empty(rows, dtype=torch.float64, device="cuda")
     op.multiply_device(xv, yv, reps=5)
-    barrier()
-    spmv_ms = max_over_ranks(op.multiply_device(xv, yv, reps=args.spmv_reps))
+    env.barrier()
+    spmv_ms = env.max_over_ranks(op.multiply_device(xv, yv, reps=args.spmv_reps))
     spmv_bytes = 12 * nnz_global + 4 * (rows_global + 1) + 16 * rows_global
-    peak, peak_src = measured_peak_gbs()
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     it_bytes = iteration_bytes(nnz_global, rows_global, solver)
     it_gbs = it_bytes * iters_total / (dev_ms * 1e-3) / 1e9
@@ -290,24 +406,49 @@ def run_ours(args):
         except Exception:
             traffic = None
 
-    # ---- parity guard: the solve converged and the true residual is below tol (checked on rank 0 at N=1) ----
-    if world == 1 and not args.skip_check:
+    # ---- parity guards: converged, and the true residual (distributed product, norms summed over ranks) below tol ----
+    true_res = None
+    if not args.skip_check:
         s.solve_device(b_dev, x_dev)
-        r_dev = torch.empty_like(x_dev)
-        op.multiply_device(x_dev, r_dev, reps=1)
-        true_res = float(torch.linalg.norm(b_dev - r_dev) / torch.linalg.norm(b_dev))
+        true_res = true_residual(env, op, b_dev, x_dev)
 
-    cpu_baseline = None
+    # ---- CPU reference leg (rank 0, N=1): timed, and its x after m iterations compared with the GPU's at the same m ----
+    cpu_baseline, parity_k = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             m = args.ref_iters or max(4, int(round(60 * (256 / n) ** 3)))
-            R, Af, bf, threads = cpu_reference_run(n, solver, m)
+            R, Af, bf, threads = cpu_reference_problem(n, solver)
             fnr = R.cg if solver == "cg" else R.bicgstab
-            _, itc, _, _ = fnr(Af, bf, tol=TOL, max_iters=m, threads=threads)
+            x_cpu, itc, err_cpu, _ = fnr(Af, bf, tol=TOL, max_iters=m, threads=threads)
             cpu_baseline = {"value": itc / R.last_solve_seconds, "unit": UNIT, "cores": threads, "kind": "reference",
                             "sample": f"{itc} iterations of the same solve (setMaxIterations({m})); {R.build_info}"}
+            s.setMaxIterations(m)
+            s.solve_device(b_dev, x_dev)
+            x_gpu = x_dev.cpu().numpy()
+            parity_k = {"k": m, "rel_x": float(np.linalg.norm(x_gpu - x_cpu) / np.linalg.norm(x_cpu)),
+                        "iterations": [int(s.iterations()), int(itc)], "error": [s.error(), err_cpu]}
+            s.setMaxIterations(-1)
+            del Af, bf, x_cpu
         except Exception as e:  # the checker is optional at run time; say so rather than fail the bench
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e!r}"}
+
+    s.close()
+    op.close()
+    del b_dev, x_dev, xv, yv, A, P
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations, same protocol (extra keys) ----
+    configs = {}
+    if not args.no_extras:
+        try:
+            if world == 1 and solver == "cg" and n == 256:
+                configs["bicgstab_256"] = side_config(env, egm, 256, "bicgstab", 3, max(2, args.steps // 4), 3, peak)
+                configs["poisson2d_1024"] = side_config(env, egm, 1024, "cg", 2, max(2, args.steps // 4), 3, peak)
+                configs["spmv_sweep"] = spmv_sweep(env, egm, args.sweep_rows, peak)
+            if world == 8 and solver == "cg" and n == 256:
+                configs["poisson3d_512"] = side_config(env, egm, 512, "cg", 3, 3, 3, peak)
+        except Exception as e:
+            configs["error"] = repr(e)
 
     if rank == 0:
         line = {
@@ -318,8 +459,9 @@ def run_ours(args):
                        "parallelism": f"row-block x{world}" if world > 1 else "single GPU",
                        "l2": "working set per iteration (3.2 GB at 256^3) exceeds L2; no explicit flush",
                        "iterations_per_solve": iters, "error": err, "info": info, "true_residual": true_res,
+                       "parity_k_rel": parity_k,
                        "loop_mode": stats["loop_mode"], "evict_first": stats["evict_first"], "spmv_grid": stats["spmv_grid"],
-                       "spmv_stages": stats["spmv_stages"], "setup_s": round(t_setup, 2)},
+                       "spmv_stages": stats["spmv_stages"], "setup_s": round(setup_s, 2)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rows * 8) * world,
                     "d2h_bytes_per_step": int(rows * 8) * world, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
@@ -334,14 +476,12 @@ def run_ours(args):
             "timeline_rank0": timeline,
             "clocks": clocks,
             "cpu_baseline": cpu_baseline,
+            "configs": configs,
         }
         print(json.dumps(line))
-    s.close()
-    op.close()
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    if env.dist:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
     return 0
 
 
@@ -357,6 +497,10 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-check", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the non-headline BASELINE configurations")
+    ap.add_argument("--sweep-rows", type=int, default=1 << 20,
+                    help="rows of the banded / power-law matrices of the SpMV sweep (SURVEY 8d names 2^22; the default "
+                         "keeps the default run within minutes -- matrix generation on the host dominates)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -30,7 +30,8 @@ class Stats(C.Structure):
         ("sm_count", C.c_int32),
         ("last_solve_ms", C.c_double), ("last_h2d_ms", C.c_double), ("last_d2h_ms", C.c_double),
         ("last_kernel_launches", C.c_int64), ("last_iterations", C.c_int64), ("last_spmv_count", C.c_int64),
-        ("device_bytes", C.c_int64),
+        ("device_bytes", C.c_int64), ("last_restarts", C.c_int64), ("last_nonfinite", C.c_int32),
+        ("last_comm_error", C.c_int32),
     ]
 
     def as_dict(self):
@@ -70,9 +71,10 @@ def lib() -> C.CDLL:
         getattr(L, f"b200s_spmv_{sfx}").argtypes = [H, vp, vp]
         getattr(L, f"b200s_spmv_device_{sfx}").argtypes = [H, vp, vp, C.c_int, C.POINTER(C.c_float)]
     solve_args = [H, vp, vp, C.c_int, dbl, i64, C.POINTER(i64), C.POINTER(dbl), C.POINTER(C.c_int)]
-    for name in ("b200s_cg_solve_f64", "b200s_bicgstab_solve_f64", "b200s_cg_solve_device_f64",
-                 "b200s_bicgstab_solve_device_f64"):
-        getattr(L, name).argtypes = solve_args
+    for sfx in ("f64", "f32"):
+        for name in ("b200s_cg_solve_", "b200s_bicgstab_solve_", "b200s_cg_solve_device_",
+                     "b200s_bicgstab_solve_device_"):
+            getattr(L, name + sfx).argtypes = solve_args
     L.b200s_get_stats.argtypes = [H, C.POINTER(Stats)]
     L.b200s_get_invdiag_f64.argtypes = [H, vp]
     L.b200s_get_timeline.argtypes = [H, vp, C.c_int]
@@ -83,6 +85,8 @@ def lib() -> C.CDLL:
     L.b200s_plan_probe.restype = i64
     L.b200s_plan_probe_csr.argtypes = [i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64]
     L.b200s_plan_probe_csr.restype = i64
+    L.b200s_plan_probe_span.argtypes = [i64, i64, vp, vp, vp, C.c_int]
+    L.b200s_plan_probe_span.restype = i64
     _lib = L
     return L
 

@@ -66,8 +66,9 @@ struct b200s_handle {
   std::vector<int64_t> all_rows, all_ghosts;
   DevBuf b, r, q, r0, s, t, yout;
   DevBuf scalars, partials, counter, halo_counter, history, gridbar;
-  int persist_grid = 0;
+  int persist_grid = 0, persist_grid_f32 = 0;
   Scalars* hS = nullptr;  // pinned mirror
+  double comm_timeout_ms = 20000.0;  // bound of every device-side wait on a peer (B200S_COMM_TIMEOUT_MS)
   // launch geometry
   int spmv_grid = 0, spmv_stages = 0, spmv_smem = 0, vec_grid = 0;
   int spmv_grid_f32 = 0, spmv_smem_f32 = 0;  // float tiles are smaller: more CTAs fit per SM
@@ -78,7 +79,8 @@ struct b200s_handle {
   size_t device_bytes = 0;
   // stats of the last call
   double last_solve_ms = 0, last_h2d_ms = 0, last_d2h_ms = 0;
-  int64_t last_launches = 0, last_iterations = 0, last_spmv = 0;
+  int64_t last_launches = 0, last_iterations = 0, last_spmv = 0, last_restarts = 0;
+  int last_nonfinite = 0, last_comm_error = 0;
 };
 
 namespace {
@@ -185,6 +187,7 @@ RedCtx make_red(const b200s_handle* h, int epilogue, int gate, bool set_cond, cu
   r.cond_handle = static_cast<unsigned long long>(cond);
   r.set_cond = set_cond ? 1 : 0;
   r.comm = make_comm(h);
+  r.f32 = (h->scalar_bytes == 4) ? 1 : 0;
   return r;
 }
 
@@ -306,20 +309,21 @@ int launch_spmv_args(b200s_handle* h, const SpmvArgs<T>& a, int ndot) {
   return 0;
 }
 
-VecArgs make_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGraphConditionalHandle cond) {
-  VecArgs a{};
+template <typename T>
+VecArgsT<T> make_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGraphConditionalHandle cond) {
+  VecArgsT<T> a{};
   a.n = h->plan.rows;
-  a.x = slot_ptr<double>(h, kSlotX);
-  a.p = slot_ptr<double>(h, kSlotP);  // CG: p ; BiCGSTAB: y lives in kSlotP, p in h->yout (not exchanged)
-  a.z = slot_ptr<double>(h, kSlotZ);
-  a.r = h->r.as<double>();
-  a.q = h->q.as<double>();
-  a.r0 = h->r0.as<double>();
-  a.s = h->s.as<double>();
-  a.t = h->t.as<double>();
+  a.x = slot_ptr<T>(h, kSlotX);
+  a.p = slot_ptr<T>(h, kSlotP);  // CG: p ; BiCGSTAB: y lives in kSlotP, p in h->yout (not exchanged)
+  a.z = slot_ptr<T>(h, kSlotZ);
+  a.r = h->r.as<T>();
+  a.q = h->q.as<T>();
+  a.r0 = h->r0.as<T>();
+  a.s = h->s.as<T>();
+  a.t = h->t.as<T>();
   a.y = nullptr;
-  a.b = h->b.as<double>();
-  a.invdiag = h->invdiag.as<double>();
+  a.b = h->b.as<T>();
+  a.invdiag = h->invdiag.as<T>();
   a.history = h->history.as<double>();
   a.red = make_red(h, epilogue, gate, set_cond, cond);
   return a;
@@ -333,97 +337,102 @@ VecArgs make_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGra
   } while (0)
 
 // ---- the iteration bodies (enqueued either under stream capture or directly) ----
+template <typename T>
 int enqueue_cg_init(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
   int rc;
-  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotX), h->q.as<double>(), nullptr, 0, kEpiNone, kGateGuess,
-                                false, 0, kSlotX)))
+  if ((rc = launch_spmv<T>(h, slot_ptr<T>(h, kSlotX), h->q.as<T>(), nullptr, 0, kEpiNone, kGateGuess, false, 0, kSlotX)))
     return rc;
-  VecArgs a = make_vec(h, kEpiCgInit, kGateNone, set_cond, cond);
-  LAUNCH_VEC(cg_init_kernel, a);
+  VecArgsT<T> a = make_vec<T>(h, kEpiCgInit, kGateNone, set_cond, cond);
+  LAUNCH_VEC(cg_init_kernel<T>, a);
   return 0;
 }
 
+template <typename T>
 int enqueue_cg_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
   int rc;
-  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotP), h->q.as<double>(), nullptr, 1, kEpiCgPAp, kGateLoop,
-                                false, 0, kSlotP)))
+  if ((rc = launch_spmv<T>(h, slot_ptr<T>(h, kSlotP), h->q.as<T>(), nullptr, 1, kEpiCgPAp, kGateLoop, false, 0, kSlotP)))
     return rc;
-  VecArgs u = make_vec(h, kEpiCgUpdate, kGateLoop, set_cond, cond);
-  LAUNCH_VEC(cg_update_kernel, u);
-  VecArgs d = make_vec(h, kEpiNone, kGateNone, false, 0);
-  CK(launch_k(h, cg_direction_kernel, h->vec_grid, kVecThreads, 0, d, h->gridbar.as<unsigned>() + 64));
+  VecArgsT<T> u = make_vec<T>(h, kEpiCgUpdate, kGateLoop, set_cond, cond);
+  LAUNCH_VEC(cg_update_kernel<T>, u);
+  VecArgsT<T> d = make_vec<T>(h, kEpiNone, kGateNone, false, 0);
+  CK(launch_k(h, cg_direction_kernel<T>, h->vec_grid, kVecThreads, 0, d, h->gridbar.as<unsigned>() + 64));
   h->last_launches++;
   return 0;
 }
 
 // The whole CG loop as one cooperative kernel (B200S_LOOP_PERSISTENT).
+template <typename T>
 int launch_cg_persistent(b200s_handle* h) {
-  CgPersistArgs a{};
-  int rc = make_spmv_args<double>(h, a.sp, slot_ptr<double>(h, kSlotP), h->q.as<double>(), nullptr, kEpiCgPAp,
-                                  kGateNone, false, 0, kSlotP);
+  CgPersistArgs<T> a{};
+  int rc = make_spmv_args<T>(h, a.sp, slot_ptr<T>(h, kSlotP), h->q.as<T>(), nullptr, kEpiCgPAp, kGateNone, false, 0,
+                             kSlotP);
   if (rc) return rc;
-  if (a.sp.halo.enabled) a.sp.halo.npush = std::min(a.sp.halo.npush, h->persist_grid);
-  a.ve = make_vec(h, kEpiCgUpdate, kGateNone, false, 0);
+  const int grid = sizeof(T) == 4 ? h->persist_grid_f32 : h->persist_grid;
+  if (a.sp.halo.enabled) a.sp.halo.npush = std::min(a.sp.halo.npush, grid);
+  a.ve = make_vec<T>(h, kEpiCgUpdate, kGateNone, false, 0);
   a.bar_count = h->gridbar.as<unsigned>();
   a.bar_gen = h->gridbar.as<unsigned>() + 1024;  // 4 KB away from the arrival counter: a different L2 slice
   void* params[] = {&a};
-  CK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(h->persist_grid), dim3(kSpmvThreads), params,
-                                 static_cast<size_t>(h->spmv_smem), h->stream));
+  CK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel<T>, dim3(grid), dim3(kSpmvThreads), params,
+                                 static_cast<size_t>(sizeof(T) == 4 ? h->spmv_smem_f32 : h->spmv_smem), h->stream));
   h->last_launches++;
   return 0;
 }
 
 // BiCGSTAB vector roles: x = slot X (ext), y = slot P (ext), z = slot Z (ext), p = h->yout, v = h->q, t = h->t
-VecArgs make_bicg_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGraphConditionalHandle cond) {
-  VecArgs a = make_vec(h, epilogue, gate, set_cond, cond);
-  a.y = slot_ptr<double>(h, kSlotP);
-  a.p = h->yout.as<double>();
+template <typename T>
+VecArgsT<T> make_bicg_vec(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGraphConditionalHandle cond) {
+  VecArgsT<T> a = make_vec<T>(h, epilogue, gate, set_cond, cond);
+  a.y = slot_ptr<T>(h, kSlotP);
+  a.p = h->yout.as<T>();
   return a;
 }
 
+template <typename T>
 int enqueue_bicg_init(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
   int rc;
-  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotX), h->t.as<double>(), nullptr, 0, kEpiNone, kGateGuess,
-                                false, 0, kSlotX)))
+  if ((rc = launch_spmv<T>(h, slot_ptr<T>(h, kSlotX), h->t.as<T>(), nullptr, 0, kEpiNone, kGateGuess, false, 0, kSlotX)))
     return rc;
-  VecArgs a = make_bicg_vec(h, kEpiBiInit, kGateNone, set_cond, cond);
-  LAUNCH_VEC(bicg_init_kernel, a);
+  VecArgsT<T> a = make_bicg_vec<T>(h, kEpiBiInit, kGateNone, set_cond, cond);
+  LAUNCH_VEC(bicg_init_kernel<T>, a);
   return 0;
 }
 
+template <typename T>
 int enqueue_bicg_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
   int rc;
   // re-orthogonalisation branch (BiCGSTAB.h:72-81), live only when the control state asks for it
-  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotX), h->t.as<double>(), nullptr, 0, kEpiNone,
-                                kGateRestart, false, 0, kSlotX)))
+  if ((rc = launch_spmv<T>(h, slot_ptr<T>(h, kSlotX), h->t.as<T>(), nullptr, 0, kEpiNone, kGateRestart, false, 0,
+                           kSlotX)))
     return rc;
-  VecArgs rs = make_bicg_vec(h, kEpiBiRestart, kGateRestart, false, 0);
-  LAUNCH_VEC(bicg_restart_kernel, rs);
-  VecArgs pa = make_bicg_vec(h, kEpiNone, kGateLoop, false, 0);
-  LAUNCH_VEC(bicg_p_kernel, pa);
-  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotP), h->q.as<double>(), h->r0.as<double>(), 1, kEpiBiR0V,
-                                kGateLoop, false, 0, kSlotP)))
+  VecArgsT<T> rs = make_bicg_vec<T>(h, kEpiBiRestart, kGateRestart, false, 0);
+  LAUNCH_VEC(bicg_restart_kernel<T>, rs);
+  VecArgsT<T> pa = make_bicg_vec<T>(h, kEpiNone, kGateLoop, false, 0);
+  LAUNCH_VEC(bicg_p_kernel<T>, pa);
+  if ((rc = launch_spmv<T>(h, slot_ptr<T>(h, kSlotP), h->q.as<T>(), h->r0.as<T>(), 1, kEpiBiR0V, kGateLoop, false, 0,
+                           kSlotP)))
     return rc;
-  VecArgs sa = make_bicg_vec(h, kEpiNone, kGateLoop, false, 0);
-  LAUNCH_VEC(bicg_s_kernel, sa);
-  if ((rc = launch_spmv<double>(h, slot_ptr<double>(h, kSlotZ), h->t.as<double>(), h->s.as<double>(), 2, kEpiBiTsTt,
-                                kGateLoop, false, 0, kSlotZ)))
+  VecArgsT<T> sa = make_bicg_vec<T>(h, kEpiNone, kGateLoop, false, 0);
+  LAUNCH_VEC(bicg_s_kernel<T>, sa);
+  if ((rc = launch_spmv<T>(h, slot_ptr<T>(h, kSlotZ), h->t.as<T>(), h->s.as<T>(), 2, kEpiBiTsTt, kGateLoop, false, 0,
+                           kSlotZ)))
     return rc;
-  VecArgs ua = make_bicg_vec(h, kEpiBiUpdate, kGateLoop, set_cond, cond);
-  LAUNCH_VEC(bicg_update_kernel, ua);
+  VecArgsT<T> ua = make_bicg_vec<T>(h, kEpiBiUpdate, kGateLoop, set_cond, cond);
+  LAUNCH_VEC(bicg_update_kernel<T>, ua);
   return 0;
 }
 
+template <typename T>
 int enqueue_finalize(b200s_handle* h) {
-  VecArgs a = make_vec(h, kEpiNone, kGateNone, false, 0);
-  LAUNCH_VEC(finalize_kernel, a);
+  VecArgsT<T> a = make_vec<T>(h, kEpiNone, kGateNone, false, 0);
+  LAUNCH_VEC(finalize_kernel<T>, a);
   return 0;
 }
 
 typedef int (*enqueue_fn)(b200s_handle*, bool, cudaGraphConditionalHandle);
 
 // Builds the solve graph(s) for one solver kind.
-int build_graphs(b200s_handle* h, GraphSet& g, enqueue_fn init, enqueue_fn body) {
+int build_graphs(b200s_handle* h, GraphSet& g, enqueue_fn init, enqueue_fn body, int (*finalize)(b200s_handle*)) {
   if (g.built) return 0;
   int64_t saved = h->last_launches;
   if (h->loop_mode == B200S_LOOP_WHILE_GRAPH || h->loop_mode == B200S_LOOP_PERSISTENT) {
@@ -466,7 +475,7 @@ int build_graphs(b200s_handle* h, GraphSet& g, enqueue_fn init, enqueue_fn body)
     // 3. tail
     CK(cudaStreamBeginCaptureToGraph(h->stream, g.graph, &while_node, nullptr, 1, cudaStreamCaptureModeRelaxed));
     h->last_launches = 0;
-    rc = enqueue_finalize(h);
+    rc = finalize(h);
     g.tail_kernels = static_cast<int>(h->last_launches);
     ee = cudaStreamEndCapture(h->stream, &tmp);
     if (rc) return rc;
@@ -514,37 +523,66 @@ int ensure_solver_buffers(b200s_handle* h, bool bicg) {
   return 0;
 }
 
-int run_solve(b200s_handle* h, bool bicg, const double* b_dev, double* x_dev, int use_guess, double tol,
-              int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out) {
-  if (!h->factorized) return fail(h, B200S_ERR_INVALID, "solve: call analyze_pattern + factorize first (IterativeSolverBase.h:337 asserts m_isInitialized)");
-  if (h->scalar_bytes != 8) return fail(h, B200S_ERR_UNSUPPORTED, "solve: the matrix was factorized in float; solvers run in double");
-  int rc;
-  if ((rc = ensure_solver_buffers(h, bicg))) return rc;
-  GraphSet& g = bicg ? h->bicg : h->cg;
-  if ((rc = build_graphs(h, g, bicg ? enqueue_bicg_init : enqueue_cg_init, bicg ? enqueue_bicg_body : enqueue_cg_body)))
-    return rc;
+// Row-partitioned runs: all ranks agree that everybody got this far before anything that waits on a peer is
+// launched (a rank that failed on the host would otherwise leave the others spinning until the device-side timeout).
+int agree_to_launch(b200s_handle* h, int my_rc) {
+  if (h->plan.world <= 1 || !h->cfg.allgather) return my_rc;
+  int64_t mine = my_rc;
+  std::vector<int64_t> all(h->plan.world, 0);
+  if (h->cfg.allgather(h->cfg.allgather_ctx, &mine, all.data(), sizeof(mine)))
+    return my_rc ? my_rc : fail(h, B200S_ERR_COMM, "allgather(status before launch) failed");
+  if (my_rc) return my_rc;
+  for (int q = 0; q < h->plan.world; ++q)
+    if (all[q] != 0)
+      return fail(h, B200S_ERR_COMM, "rank " + std::to_string(q) + " failed before the launch (status " +
+                                         std::to_string(all[q]) + "); nothing was launched on this rank");
+  return 0;
+}
 
-  const int64_t n = h->plan.rows;
-  if (tol < 0) tol = std::numeric_limits<double>::epsilon();  // IterativeSolverBase.h:413
-  if (max_iters < 0) max_iters = 2 * h->plan.cols;             // :281-284
-  double* x_int = slot_ptr<double>(h, kSlotX);
-  if (b_dev != h->b.as<double>()) CK(cudaMemcpyAsync(h->b.p, b_dev, n * 8, cudaMemcpyDeviceToDevice, h->stream));
-  if (use_guess && x_dev != x_int) CK(cudaMemcpyAsync(x_int, x_dev, n * 8, cudaMemcpyDeviceToDevice, h->stream));
-  // solve inputs -> device control block (first 24 bytes of Scalars)
+int push_solve_inputs(b200s_handle* h, double tol, int64_t max_iters, int use_guess) {
   h->hS->tol = tol;
   h->hS->max_iters = max_iters;
   h->hS->use_guess = use_guess ? 1 : 0;
-  h->hS->pad0 = 0;
-  CK(cudaMemcpyAsync(h->scalars.p, h->hS, 24, cudaMemcpyHostToDevice, h->stream));
+  h->hS->comm_error = 0;
+  h->hS->comm_timeout_ns = static_cast<unsigned long long>(h->comm_timeout_ms * 1e6);
+  CK(cudaMemcpyAsync(h->scalars.p, h->hS, kSolveInputBytes, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+template <typename T>
+int run_solve(b200s_handle* h, bool bicg, const T* b_dev, T* x_dev, int use_guess, double tol, int64_t max_iters,
+              int64_t* iters_out, double* error_out, int* info_out) {
+  int rc = 0;
+  if (!h->factorized)
+    rc = fail(h, B200S_ERR_INVALID, "solve: call analyze_pattern + factorize first (IterativeSolverBase.h:337 asserts m_isInitialized)");
+  else if (h->scalar_bytes != static_cast<int>(sizeof(T)))
+    rc = fail(h, B200S_ERR_INVALID, "solve: scalar type differs from the one given to factorize");
+  else if (h->plan.world == 1 && h->plan.rows != h->plan.cols)
+    rc = fail(h, B200S_ERR_INVALID, "solve: the matrix is not square");
+  GraphSet& g = bicg ? h->bicg : h->cg;
+  if (!rc) rc = ensure_solver_buffers(h, bicg);
+  if (!rc)
+    rc = build_graphs(h, g, bicg ? enqueue_bicg_init<T> : enqueue_cg_init<T>, bicg ? enqueue_bicg_body<T> : enqueue_cg_body<T>,
+                      enqueue_finalize<T>);
+  if ((rc = agree_to_launch(h, rc))) return rc;
+
+  const int64_t n = h->plan.rows;
+  if (tol < 0) tol = std::numeric_limits<T>::epsilon();       // IterativeSolverBase.h:413
+  if (sizeof(T) == 4) tol = static_cast<double>(static_cast<float>(tol));  // RealScalar m_tolerance
+  if (max_iters < 0) max_iters = 2 * h->plan.cols;             // :281-284
+  T* x_int = slot_ptr<T>(h, kSlotX);
+  if (b_dev != h->b.as<T>()) CK(cudaMemcpyAsync(h->b.p, b_dev, n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+  if (use_guess && x_dev != x_int) CK(cudaMemcpyAsync(x_int, x_dev, n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+  if ((rc = push_solve_inputs(h, tol, max_iters, use_guess))) return rc;
 
   h->last_launches = 0;
   CK(cudaEventRecord(h->ev0, h->stream));
   const bool persistent = (h->loop_mode == B200S_LOOP_PERSISTENT) && !bicg && h->spmv_impl != B200S_SPMV_DIRECT;
   const bool while_graph = (h->loop_mode == B200S_LOOP_WHILE_GRAPH) || (h->loop_mode == B200S_LOOP_PERSISTENT && !persistent);
   if (persistent) {
-    if ((rc = enqueue_cg_init(h, false, 0))) return rc;
-    if ((rc = launch_cg_persistent(h))) return rc;
-    if ((rc = enqueue_finalize(h))) return rc;
+    if ((rc = enqueue_cg_init<T>(h, false, 0))) return rc;
+    if ((rc = launch_cg_persistent<T>(h))) return rc;
+    if ((rc = enqueue_finalize<T>(h))) return rc;
   } else if (while_graph) {
     CK(cudaGraphLaunch(g.exec, h->stream));
   } else {
@@ -552,7 +590,7 @@ int run_solve(b200s_handle* h, bool bicg, const double* b_dev, double* x_dev, in
       CK(cudaGraphLaunch(g.exec, h->stream));
       h->last_launches += g.init_kernels;
     } else {
-      if ((rc = (bicg ? enqueue_bicg_init : enqueue_cg_init)(h, false, 0))) return rc;
+      if ((rc = (bicg ? enqueue_bicg_init<T> : enqueue_cg_init<T>)(h, false, 0))) return rc;
     }
     for (;;) {
       CK(cudaMemcpyAsync(h->hS, h->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
@@ -562,34 +600,49 @@ int run_solve(b200s_handle* h, bool bicg, const double* b_dev, double* x_dev, in
         CK(cudaGraphLaunch(g.body_exec, h->stream));
         h->last_launches += g.body_kernels;
       } else {
-        if ((rc = (bicg ? enqueue_bicg_body : enqueue_cg_body)(h, false, 0))) return rc;
+        if ((rc = (bicg ? enqueue_bicg_body<T> : enqueue_cg_body<T>)(h, false, 0))) return rc;
       }
     }
-    if ((rc = enqueue_finalize(h))) return rc;
+    if ((rc = enqueue_finalize<T>(h))) return rc;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaMemcpyAsync(h->hS, h->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
-  if (x_dev != x_int) CK(cudaMemcpyAsync(x_dev, x_int, n * 8, cudaMemcpyDeviceToDevice, h->stream));
+  if (x_dev != x_int) CK(cudaMemcpyAsync(x_dev, x_int, n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_solve_ms = ms;
 
   const Scalars& S = *h->hS;
+  h->last_comm_error = S.comm_error;
+  h->last_nonfinite = S.numerical_issue;
+  h->last_restarts = bicg ? S.restarts : 0;
+  if (S.comm_error) {
+    if (info_out) *info_out = 1;  // NumericalIssue: the result is not usable
+    return fail(h, B200S_ERR_COMM, "a device-side wait on a peer GPU expired after " + std::to_string(h->comm_timeout_ms) +
+                                       " ms (dead or diverged rank); the solve was abandoned");
+  }
   int64_t iters;
   double err;
+  auto real_sqrt_ratio = [](double rr, double bb) {  // tol_error = sqrt(residualNorm2 / rhsNorm2) in RealScalar
+    if (sizeof(T) == 4) return static_cast<double>(std::sqrt(static_cast<float>(rr) / static_cast<float>(bb)));
+    return std::sqrt(rr / bb);
+  };
   if (bicg && S.rhs_zero) {  // BiCGSTAB.h:47-51 returns before touching iters / tol_error
     iters = max_iters;
     err = tol;
   } else if (S.rhs_zero) {   // ConjugateGradient.h:46-52
     iters = 0;
     err = 0.0;
+  } else if (!bicg && S.numerical_issue) {
+    // CG on a non-finite residual: the reference iterates on NaNs until maxIters and reports that (see kEpiCgInit)
+    iters = max_iters;
+    err = std::numeric_limits<double>::quiet_NaN();
   } else {
     iters = S.iter;
-    err = std::sqrt(S.rr / S.bb);  // ConjugateGradient.h:89 / BiCGSTAB.h:104
+    err = real_sqrt_ratio(S.rr, S.bb);  // ConjugateGradient.h:89 / BiCGSTAB.h:104
   }
-  int info = (err <= tol) ? 0 : 2;  // ConjugateGradient.h:220 / BiCGSTAB.h:201-203
-  if (S.numerical_issue) info = 1;
+  int info = (err <= tol) ? 0 : 2;  // ConjugateGradient.h:220 / BiCGSTAB.h:201-203 (NaN compares false: NoConvergence)
   if (iters_out) *iters_out = iters;
   if (error_out) *error_out = err;
   if (info_out) *info_out = info;
@@ -659,9 +712,11 @@ int factorize_impl(b200s_handle* h, const T* values, int precond) {
 
 template <typename T>
 int spmv_device_impl(b200s_handle* h, const T* x_dev, T* y_dev, int reps, float* ms_avg) {
-  if (!h->factorized) return fail(h, B200S_ERR_INVALID, "spmv: call analyze_pattern + factorize first");
-  if (h->scalar_bytes != static_cast<int>(sizeof(T))) return fail(h, B200S_ERR_INVALID, "spmv: scalar type differs from factorize");
-  if (!x_dev || !y_dev) return fail(h, B200S_ERR_INVALID, "spmv: null pointer");
+  int rc = 0;
+  if (!h->factorized) rc = fail(h, B200S_ERR_INVALID, "spmv: call analyze_pattern + factorize first");
+  else if (h->scalar_bytes != static_cast<int>(sizeof(T))) rc = fail(h, B200S_ERR_INVALID, "spmv: scalar type differs from factorize");
+  else if (!x_dev || !y_dev) rc = fail(h, B200S_ERR_INVALID, "spmv: null pointer");
+  if ((rc = agree_to_launch(h, rc))) return rc;
   CK(cudaSetDevice(h->device));
   if (reps < 1) reps = 1;
   const T* x_ext = x_dev;
@@ -670,20 +725,25 @@ int spmv_device_impl(b200s_handle* h, const T* x_dev, T* y_dev, int reps, float*
     T* xs = slot_ptr<T>(h, kSlotSpmv);
     if (x_dev != xs) CK(cudaMemcpyAsync(xs, x_dev, static_cast<size_t>(h->plan.rows) * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
     x_ext = xs;
+    if ((rc = push_solve_inputs(h, 0.0, 0, 0))) return rc;  // clears comm_error, sets the wait bound
   }
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < reps; ++i) {
-    int rc;
     // multi-GPU: each launch pushes the halo, multiplies, and ends in a cross-rank rendezvous (kEpiSpmvOnly) that
     // keeps the single-buffered ghost slots safe for the next push
     if ((rc = launch_spmv<T>(h, x_ext, y_dev, nullptr, 0, kEpiNone, kGateNone, false, 0, kSlotSpmv))) return rc;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
+  if (h->plan.world > 1) CK(cudaMemcpyAsync(h->hS, h->scalars.p, kSolveInputBytes, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   if (ms_avg) *ms_avg = ms / reps;
   h->last_solve_ms = ms;
+  if (h->plan.world > 1 && h->hS->comm_error) {
+    h->last_comm_error = 1;
+    return fail(h, B200S_ERR_COMM, "spmv: a device-side wait on a peer GPU expired (dead or diverged rank)");
+  }
   return 0;
 }
 
@@ -716,36 +776,47 @@ int spmv_host_impl(b200s_handle* h, const T* x, T* y) {
   return 0;
 }
 
-int solve_host(b200s_handle* h, bool bicg, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
+template <typename T>
+int solve_host(b200s_handle* h, bool bicg, const T* b, T* x, int use_guess, double tol, int64_t max_iters,
                int64_t* iters_out, double* error_out, int* info_out) {
   if (!h) return B200S_ERR_INVALID;
-  if (!h->factorized) return fail(h, B200S_ERR_INVALID, "solve: call analyze_pattern + factorize first");
   if (!b || !x) return fail(h, B200S_ERR_INVALID, "solve: null pointer");
   CK(cudaSetDevice(h->device));
-  int rc;
-  if ((rc = ensure_solver_buffers(h, bicg))) return rc;
-  const size_t vb = static_cast<size_t>(h->plan.rows) * 8;
+  int rc = 0;
+  if (!h->factorized) rc = fail(h, B200S_ERR_INVALID, "solve: call analyze_pattern + factorize first");
+  if (!rc) rc = ensure_solver_buffers(h, bicg);
+  if (rc) return agree_to_launch(h, rc);  // let the peers know instead of leaving them waiting
+  const size_t vb = static_cast<size_t>(h->plan.rows) * sizeof(T);
   cudaEvent_t e0 = h->ev0, e1 = h->ev1;
   CK(cudaEventRecord(e0, h->stream));
   CK(cudaMemcpyAsync(h->b.p, b, vb, cudaMemcpyHostToDevice, h->stream));
-  if (use_guess) CK(cudaMemcpyAsync(slot_ptr<double>(h, kSlotX), x, vb, cudaMemcpyHostToDevice, h->stream));
+  if (use_guess) CK(cudaMemcpyAsync(slot_ptr<T>(h, kSlotX), x, vb, cudaMemcpyHostToDevice, h->stream));
   CK(cudaEventRecord(e1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e0, e1));
   h->last_h2d_ms = ms;
-  if ((rc = run_solve(h, bicg, h->b.as<double>(), slot_ptr<double>(h, kSlotX), use_guess, tol, max_iters, iters_out,
-                      error_out, info_out)))
+  if ((rc = run_solve<T>(h, bicg, h->b.as<T>(), slot_ptr<T>(h, kSlotX), use_guess, tol, max_iters, iters_out, error_out,
+                         info_out)))
     return rc;
   double solve_ms = h->last_solve_ms;
   CK(cudaEventRecord(e0, h->stream));
-  CK(cudaMemcpyAsync(x, slot_ptr<double>(h, kSlotX), vb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(x, slot_ptr<T>(h, kSlotX), vb, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(e1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaEventElapsedTime(&ms, e0, e1));
   h->last_d2h_ms = ms;
   h->last_solve_ms = solve_ms;
   return 0;
+}
+
+template <typename T>
+int solve_device(b200s_handle* h, bool bicg, const T* b, T* x, int use_guess, double tol, int64_t max_iters,
+                 int64_t* iters_out, double* error_out, int* info_out) {
+  if (!h) return B200S_ERR_INVALID;
+  if (!b || !x) return fail(h, B200S_ERR_INVALID, "solve: null pointer");
+  CK(cudaSetDevice(h->device));
+  return run_solve<T>(h, bicg, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
 }
 
 int configure_spmv(b200s_handle* h) {
@@ -784,11 +855,15 @@ int configure_spmv(b200s_handle* h) {
     h->spmv_grid_f32 = std::min(std::max(1, std::min(h->sm_count * occ32, std::max(1, ntiles))), kMaxGrid);
   }
   {
-    CK(cudaFuncSetAttribute((const void*)cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->spmv_smem));
-    int pocc = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, cg_persistent_kernel, kSpmvThreads, h->spmv_smem));
+    CK(cudaFuncSetAttribute((const void*)cg_persistent_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->spmv_smem));
+    CK(cudaFuncSetAttribute((const void*)cg_persistent_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->spmv_smem_f32));
+    int pocc = 0, pocc32 = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, cg_persistent_kernel<double>, kSpmvThreads, h->spmv_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc32, cg_persistent_kernel<float>, kSpmvThreads, h->spmv_smem_f32));
     pocc = std::min(pocc, env_int("B200S_SPMV_OCC", 8));
+    pocc32 = std::min(pocc32, env_int("B200S_SPMV_OCC", 8));
     h->persist_grid = std::max(1, std::min(h->sm_count * std::max(1, pocc), kMaxGrid));
+    h->persist_grid_f32 = std::max(1, std::min(h->sm_count * std::max(1, pocc32), kMaxGrid));
   }
   int64_t n2 = std::max<int64_t>(1, p.rows / 2);
   int64_t vg = std::min<int64_t>(static_cast<int64_t>(h->sm_count) * env_int("B200S_VEC_CTAS_PER_SM", 6),
@@ -900,6 +975,7 @@ int b200s_create(const b200s_config* cfg, b200s_handle** out) {
   // shared memory and slows the 256^3 iteration by 7 %; it only pays below 64^3.  Off by default.
   h->pdl = env_int("B200S_PDL", 0);
   h->body_unroll = std::max(1, std::min(16, env_int("B200S_BODY_UNROLL", 4)));
+  h->comm_timeout_ms = std::max(1, env_int("B200S_COMM_TIMEOUT_MS", 20000));
   if (h->cfg.tile_nnz <= 0) h->cfg.tile_nnz = env_int("B200S_TILE_NNZ", 0);
   if (h->cfg.tile_rows <= 0) h->cfg.tile_rows = env_int("B200S_TILE_ROWS", 0);
   *out = h;
@@ -964,7 +1040,8 @@ int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t n
   const int W = p.world;
   h->all_rows.assign(W, 0);
   h->all_ghosts.assign(W, 0);
-  int64_t mine[2] = {p.rows, static_cast<int64_t>(p.ghost_cols.size())};
+  // one GPU: a slot must hold an operand of the product (cols entries) as well as a result (rows entries)
+  int64_t mine[2] = {W == 1 ? std::max(p.rows, p.cols) : p.rows, static_cast<int64_t>(p.ghost_cols.size())};
   if (W > 1) {
     std::vector<int64_t> all(2 * W);
     if (h->cfg.allgather(h->cfg.allgather_ctx, mine, all.data(), sizeof(mine))) return fail(h, B200S_ERR_COMM, "allgather(rows, ghosts) failed");
@@ -973,7 +1050,7 @@ int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t n
     h->all_rows[0] = mine[0];
     h->all_ghosts[0] = mine[1];
   }
-  h->slot_bytes = ext_slot_bytes(p.rows, mine[1]);
+  h->slot_bytes = ext_slot_bytes(mine[0], mine[1]);
   h->box_off = h->slot_bytes * kNumSlots;
   h->flag_off = h->box_off + sizeof(unsigned long long) * 2 * kMaxWorld * kBoxWords;
   h->halo_flag_off = h->flag_off + sizeof(unsigned) * 2 * kMaxWorld;
@@ -1019,28 +1096,20 @@ int b200s_spmv_device_f32(b200s_handle* h, const float* x, float* y, int reps, f
   return h ? spmv_device_impl<float>(h, x, y, reps, ms) : B200S_ERR_INVALID;
 }
 
-int b200s_cg_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
-                       int64_t* iters_out, double* error_out, int* info_out) {
-  return solve_host(h, false, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
-}
-int b200s_bicgstab_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol,
-                             int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out) {
-  return solve_host(h, true, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
-}
-int b200s_cg_solve_device_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol,
-                              int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out) {
-  if (!h) return B200S_ERR_INVALID;
-  if (!b || !x) return fail(h, B200S_ERR_INVALID, "solve: null pointer");
-  CK(cudaSetDevice(h->device));
-  return run_solve(h, false, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
-}
-int b200s_bicgstab_solve_device_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol,
-                                    int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out) {
-  if (!h) return B200S_ERR_INVALID;
-  if (!b || !x) return fail(h, B200S_ERR_INVALID, "solve: null pointer");
-  CK(cudaSetDevice(h->device));
-  return run_solve(h, true, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
-}
+#define B200S_SOLVE_ENTRY(NAME, T, IMPL, BICG)                                                                      \
+  int NAME(b200s_handle* h, const T* b, T* x, int use_guess, double tol, int64_t max_iters, int64_t* iters_out,      \
+           double* error_out, int* info_out) {                                                                       \
+    return IMPL<T>(h, BICG, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);                        \
+  }
+B200S_SOLVE_ENTRY(b200s_cg_solve_f64, double, solve_host, false)
+B200S_SOLVE_ENTRY(b200s_bicgstab_solve_f64, double, solve_host, true)
+B200S_SOLVE_ENTRY(b200s_cg_solve_f32, float, solve_host, false)
+B200S_SOLVE_ENTRY(b200s_bicgstab_solve_f32, float, solve_host, true)
+B200S_SOLVE_ENTRY(b200s_cg_solve_device_f64, double, solve_device, false)
+B200S_SOLVE_ENTRY(b200s_bicgstab_solve_device_f64, double, solve_device, true)
+B200S_SOLVE_ENTRY(b200s_cg_solve_device_f32, float, solve_device, false)
+B200S_SOLVE_ENTRY(b200s_bicgstab_solve_device_f32, float, solve_device, true)
+#undef B200S_SOLVE_ENTRY
 
 int b200s_get_stats(b200s_handle* h, b200s_stats* out) {
   if (!h || !out) return B200S_ERR_INVALID;
@@ -1063,6 +1132,9 @@ int b200s_get_stats(b200s_handle* h, b200s_stats* out) {
   st.last_kernel_launches = h->last_launches;
   st.last_iterations = h->last_iterations;
   st.last_spmv_count = h->last_spmv;
+  st.last_restarts = h->last_restarts;
+  st.last_nonfinite = h->last_nonfinite;
+  st.last_comm_error = h->last_comm_error;
   st.device_bytes = static_cast<int64_t>(h->device_bytes);
   int32_t want = out->struct_size > 0 ? out->struct_size : static_cast<int32_t>(sizeof(b200s_stats));
   st.struct_size = std::min<int32_t>(want, sizeof(b200s_stats));
@@ -1158,6 +1230,21 @@ int64_t b200s_plan_probe_csr(int64_t rows, int64_t nnz, const int32_t* rowptr, c
   if (out_src)
     for (int64_t k = 0; k < n; ++k) out_src[k] = p.src.empty() ? static_cast<int32_t>(k) : p.src[k];
   return p.nnz;
+}
+
+int64_t b200s_plan_probe_span(int64_t rows, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                              const int32_t* inner_nnz, int uplo) {
+  b200s_config c;
+  std::memset(&c, 0, sizeof(c));
+  c.world = 1;
+  Plan p;
+  std::string err;
+  int rc = build_plan(c, rows, rows, nnz, rowptr, colidx, inner_nnz, uplo, nullptr, p, err);
+  if (rc) {
+    g_create_error = err;
+    return rc;
+  }
+  return p.input_nnz;
 }
 
 }  // extern "C"

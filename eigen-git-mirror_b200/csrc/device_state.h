@@ -10,6 +10,7 @@ constexpr int kVecThreads = 256;      // CTA size of the fused vector kernels
 constexpr int kMaxGrid = 2048;        // upper bound of any reduction grid (partials per reduction slot)
 constexpr int kMaxWorld = 8;          // GPUs of one NVSwitch box
 constexpr int kHistoryCap = 1 << 16;  // residual-history ring (doubles)
+constexpr int kSolveInputBytes = 32;  // leading bytes of Scalars the host writes before every solve
 
 // Solver state that lives in device memory for the whole solve.  Only "last blocks" (the CTA that takes the final
 // ticket of a reduction) and single-thread control kernels write it, so every kernel of an iteration reads a
@@ -19,7 +20,8 @@ struct Scalars {
   double tol;
   long long max_iters;
   int use_guess;
-  int pad0;
+  int comm_error;  // a bounded spin expired (dead or diverged peer): the loop was stopped, results are invalid
+  unsigned long long comm_timeout_ns;  // bound of every cross-rank / grid-wide spin (0 = default 20 s)
   // shared by CG and BiCGSTAB
   double bb;       // ||b||^2                       ConjugateGradient.h:45 / BiCGSTAB.h:46
   double thr;      // CG: max(tol^2 bb, DBL_MIN) :53-54 ; BiCGSTAB: tol^2 bb :62
@@ -97,6 +99,7 @@ struct RedCtx {
   unsigned long long cond_handle;  // cudaGraphConditionalHandle or 0
   int set_cond;                    // last block updates the WHILE condition after the epilogue
   int bump_halo;                   // the kernel carried a halo exchange (multi-GPU SpMV)
+  int f32;                         // RealScalar = float: the scalar epilogue rounds every operation to float
   CommDev comm;
 };
 

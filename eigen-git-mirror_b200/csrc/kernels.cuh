@@ -153,6 +153,22 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 
 constexpr int kBoxWords = 8;  // per (parity, source rank): up to 4 doubles as 8 tagged words
 
+// Every spin on another CTA's or another GPU's progress is bounded: when the limit expires (a peer died on the host
+// before launching, or ranks were given diverging inputs) the waiter raises comm_error + stop, the loop winds down
+// through its normal gates, and the host reports B200S_ERR_COMM instead of hanging inside a graph.
+__device__ __forceinline__ unsigned long long spin_limit_ns(const Scalars* S) {
+  const unsigned long long t = S->comm_timeout_ns;
+  return t ? t : 20000000000ull;
+}
+__device__ __forceinline__ bool spin_expired(Scalars* S, unsigned long long t0, unsigned& spins) {
+  if ((++spins & 0x3ffu) != 0) return false;
+  if (globaltimer_ns() - t0 <= spin_limit_ns(S)) return false;
+  S->comm_error = 1;
+  S->stop = 1;
+  __threadfence();
+  return true;
+}
+
 __device__ __forceinline__ void allreduce_ranks(const CommDev& c, Scalars* S, double* v, int n) {
   __shared__ unsigned s_seq;
   __shared__ double s_in[4];
@@ -180,9 +196,11 @@ __device__ __forceinline__ void allreduce_ranks(const CommDev& c, Scalars* S, do
     const unsigned long long* in =
         reinterpret_cast<const unsigned long long*>(c.box_self) + (par * kMaxWorld + peer) * kBoxWords + w;
     unsigned long long got;
+    unsigned spins = 0;
+    const unsigned long long tw = globaltimer_ns();
     do {
       got = ld_relaxed_sys_u64(in);
-    } while (static_cast<unsigned>(got >> 32) != seq);
+    } while (static_cast<unsigned>(got >> 32) != seq && !spin_expired(S, tw, spins));
     s_words[peer * kBoxWords + w] = static_cast<unsigned>(got);
   }
   __syncthreads();
@@ -203,25 +221,39 @@ __device__ __forceinline__ void allreduce_ranks(const CommDev& c, Scalars* S, do
 // --------------------------------------------------------------------------------- scalar logic of the solvers
 // Runs in exactly one thread per reduction, after the values are reduced over CTAs and ranks.  This is the
 // reference's host-side control flow moved onto the device (citations per case).
-__device__ inline void run_epilogue(const RedCtx& ctx, const double* v, double* history) {
+// RealScalar arithmetic of the reference for both instantiations: in float mode (ctx.f32) every scalar operation
+// is a float operation -- performed here in double and rounded to float after each step, which gives the same
+// result (products of two floats are exact in double; for + - / sqrt, 53 >= 2*24+2 bits make the double rounding
+// innocuous).  Reduced dot products are rounded to float once.
+__device__ __forceinline__ double rs(bool f32, double x) { return f32 ? static_cast<double>(static_cast<float>(x)) : x; }
+
+__device__ inline void run_epilogue(const RedCtx& ctx, const double* vin, double* history) {
   Scalars* S = ctx.S;
+  const bool f = ctx.f32 != 0;
+  double v[4];
+  for (int j = 0; j < 4; ++j) v[j] = rs(f, vin[j]);
+  const double real_min = f ? static_cast<double>(FLT_MIN) : DBL_MIN;
+  const double real_eps = f ? static_cast<double>(FLT_EPSILON) : DBL_EPSILON;
   switch (ctx.epilogue) {
     case kEpiCgInit: {  // ConjugateGradient.h:45-67
       const double bb = v[0], rr = v[1], rz = v[2];
       S->bb = bb; S->rr = rr; S->iter = 0; S->converged = 0; S->rhs_zero = 0; S->stop = 0; S->numerical_issue = 0;
       S->hist_len = 0; S->spmv_count = S->use_guess ? 1 : 0; S->n_update = 0; S->n_xapplied = 0;
       if (bb == 0.0) { S->rhs_zero = 1; S->stop = 1; S->rr = 0.0; break; }   // :46-52 (error = 0)
-      double thr = S->tol * S->tol * bb;                                      // :53-54
-      if (thr < DBL_MIN) thr = DBL_MIN;
+      double thr = rs(f, rs(f, S->tol * S->tol) * bb);                        // :53-54
+      if (thr < real_min) thr = real_min;
       S->thr = thr;
       if (rr < thr) { S->stop = 1; S->converged = 1; break; }                 // :56-61
       S->abs_new = rz;                                                        // :67
-      if (!(rr == rr) || !(bb == bb)) { S->numerical_issue = 1; S->stop = 1; }
+      // A non-finite norm can never pass `rr < thr`: the reference would spin through all maxIters iterations on NaNs
+      // and return NoConvergence with iters = maxIters, error = NaN and an all-NaN x (one iteration spreads the NaN
+      // through alpha).  The loop stops here instead and the host reports exactly those outputs.
+      if (!(rr == rr) || !(bb == bb)) { S->numerical_issue = (S->max_iters >= 1) ? 2 : 1; S->stop = 1; }
       if (S->max_iters <= 0) S->stop = 1;                                     // while(i < maxIters) never entered
     } break;
     case kEpiCgPAp: {  // :73
       S->pAp = v[0];
-      S->alpha = S->abs_new / v[0];
+      S->alpha = rs(f, S->abs_new / v[0]);
       S->spmv_count++;
     } break;
     case kEpiCgUpdate: {  // :77-87
@@ -230,11 +262,15 @@ __device__ inline void run_epilogue(const RedCtx& ctx, const double* v, double* 
       S->n_update++;  // x += alpha p of this iteration is still owed (applied by the direction pass)
       if (history && S->hist_len < kHistoryCap) history[S->hist_len++] = rr;
       if (rr < S->thr) { S->stop = 1; S->converged = 1; break; }  // :78-79 break before i++
-      if (!(rr == rr)) { S->numerical_issue = 1; S->stop = 1; break; }
+      if (!(rr == rr)) {  // see kEpiCgInit: two more reference iterations would turn all of x into NaN
+        S->numerical_issue = (S->max_iters - S->iter >= 2) ? 2 : 1;
+        S->stop = 1;
+        break;
+      }
       S->abs_old = S->abs_new;
-      S->abs_new = rz;                  // :84
-      S->beta = rz / S->abs_old;        // :85
-      S->iter++;                        // :87
+      S->abs_new = rz;                        // :84
+      S->beta = rs(f, rz / S->abs_old);       // :85
+      S->iter++;                              // :87
       if (S->iter >= S->max_iters) S->stop = 1;
     } break;
     case kEpiBiInit: {  // BiCGSTAB.h:45-65
@@ -243,20 +279,20 @@ __device__ inline void run_epilogue(const RedCtx& ctx, const double* v, double* 
       S->stop = 0; S->numerical_issue = 0; S->restart = 0; S->hist_len = 0; S->spmv_count = 1;
       if (bb == 0.0) { S->rhs_zero = 1; S->stop = 1; break; }  // :47-51 (iters / tol_error untouched)
       S->rho_old = 1.0; S->alpha = 1.0; S->w = 1.0;            // :52-54
-      S->thr = S->tol * S->tol * bb;                           // :62
-      S->eps2 = DBL_EPSILON * DBL_EPSILON;                     // :63
+      S->thr = rs(f, rs(f, S->tol * S->tol) * bb);             // :62
+      S->eps2 = rs(f, real_eps * real_eps);                    // :63
       if (!(rr > S->thr && 0 < S->max_iters)) { S->stop = 1; S->converged = !(rr > S->thr); break; }  // :67
       S->rho = rr;                                             // :71 r0.dot(r) with r0 == r
-      S->restart = (fabs(S->rho) < S->eps2 * S->r0_sqnorm) ? 1 : 0;  // :72
+      S->restart = (fabs(S->rho) < rs(f, S->eps2 * S->r0_sqnorm)) ? 1 : 0;  // :72
     } break;
     case kEpiBiR0V: {  // :89
       S->r0v = v[0];
-      S->alpha = S->rho / v[0];
+      S->alpha = rs(f, S->rho / v[0]);
       S->spmv_count++;
     } break;
     case kEpiBiTsTt: {  // :95-99
       S->ts = v[0]; S->tt = v[1];
-      S->w = (v[1] > 0.0) ? v[0] / v[1] : 0.0;
+      S->w = (v[1] > 0.0) ? rs(f, v[0] / v[1]) : 0.0;
       S->spmv_count++;
     } break;
     case kEpiBiUpdate: {  // :100-102 then the loop head :67-72 of the next iteration
@@ -267,7 +303,7 @@ __device__ inline void run_epilogue(const RedCtx& ctx, const double* v, double* 
       if (!(rr > S->thr && S->iter < S->max_iters)) { S->stop = 1; S->converged = !(rr > S->thr); break; }
       S->rho_old = S->rho;
       S->rho = rho_next;
-      S->restart = (fabs(S->rho) < S->eps2 * S->r0_sqnorm) ? 1 : 0;
+      S->restart = (fabs(S->rho) < rs(f, S->eps2 * S->r0_sqnorm)) ? 1 : 0;
     } break;
     case kEpiBiRestart: {  // :76-80
       S->rho = S->r0_sqnorm = v[0];
@@ -337,6 +373,7 @@ __device__ __forceinline__ void finish_reduction(const RedCtx& ctx, double (&v)[
     if (ctx.bump_halo) ctx.S->halo_seq++;  // this kernel carried a halo exchange: retire its sequence number
     timeline_mark(ctx.S, ctx.epilogue);
     run_epilogue(ctx, r, history);
+    if (ctx.S->comm_error) ctx.S->stop = 1;  // an expired spin ends the loop whatever the epilogue decided
     if (ctx.set_cond) cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(ctx.cond_handle), ctx.S->stop ? 0u : 1u);
   }
 }
@@ -384,12 +421,14 @@ __device__ __forceinline__ void halo_push(const HaloArgs<T>& hl, const CommDev& 
   }
 }
 
-__device__ __forceinline__ void halo_wait(const CommDev& c, const Scalars* S, unsigned recv_mask) {
+__device__ __forceinline__ void halo_wait(const CommDev& c, Scalars* S, unsigned recv_mask) {
   const unsigned want = S->halo_seq + 1;
+  unsigned spins = 0;
+  const unsigned long long tw = globaltimer_ns();
   for (int src = 0; src < c.world; ++src)
     if (recv_mask & (1u << src))
-      while (static_cast<int>(ld_acquire_sys(c.halo_flag_self + src) - want) < 0) {
-      }
+      while (static_cast<int>(ld_acquire_sys(c.halo_flag_self + src) - want) < 0)
+        if (spin_expired(S, tw, spins)) return;
 }
 
 // ------------------------------------------------------------------------------------------- staged CSR SpMV
@@ -763,79 +802,129 @@ __global__ void gather_values_kernel(long long n, const int32_t* __restrict__ sr
 }
 
 // ------------------------------------------------------------------------------------------ fused vector passes
-struct VecArgs {
+// Templated on the scalar type: ConjugateGradient<SparseMatrix<float>> / BiCGSTAB<SparseMatrix<float>> are plain
+// instantiations of the same templates in the reference (ConjugateGradient.h:157-160), and so they are here.  Vectors
+// and the elementwise arithmetic are in T; dot products accumulate in double (for float operands the products are
+// then exact) and are rounded to RealScalar once, in run_epilogue.
+template <typename T>
+struct VecArgsT {
   long long n;
-  double* x;
-  double* r;
-  double* p;
-  double* q;        // Ap (CG) / v (BiCGSTAB)
-  double* y;
-  double* z;
-  double* s;
-  double* t;
-  double* r0;
-  const double* b;
-  const double* invdiag;
+  T* x;
+  T* r;
+  T* p;
+  T* q;        // Ap (CG) / v (BiCGSTAB)
+  T* y;
+  T* z;
+  T* s;
+  T* t;
+  T* r0;
+  const T* b;
+  const T* invdiag;
   double* history;
   RedCtx red;
 };
 
-// Elements are dealt to threads in pairs (128-bit accesses) in a fixed grid-stride order; an odd tail element is
-// taken by thread 0 of CTA 0.  f2(i2) handles elements 2*i2 and 2*i2+1, f1(i) a single element.
-template <typename F2, typename F1>
-__device__ __forceinline__ void vec_loop(long long n, F2 f2, F1 f1) {
-  // Two pairs per thread and trip: twice the bytes in flight per thread (the order in which a thread visits its
-  // elements, hence every reduction, is unchanged).
-  constexpr int U = 2;
-  const long long n2 = n >> 1;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i2 < n2; i2 += U * stride) {
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (i2 + u * stride < n2) f2(i2 + u * stride);
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) f1(n - 1);
-}
+// 128-bit packs: two doubles or four floats.
+template <typename T>
+struct Pack;
+template <>
+struct Pack<double> {
+  static constexpr int N = 2;
+  double v[2];
+};
+template <>
+struct Pack<float> {
+  static constexpr int N = 4;
+  float v[4];
+};
 
 // Streaming 128-bit load: the vector passes touch every element exactly once, so lines are not allocated in L1
 // (in the persistent kernel L1 is only what the 4 x 52 KB shared-memory rings leave over).
-__device__ __forceinline__ double2 ld2(const double* p, long long i2) {
-  double2 v;
+__device__ __forceinline__ Pack<double> ldp(const double* p, long long ip) {
+  Pack<double> v;
   asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
-               : "=d"(v.x), "=d"(v.y)
-               : "l"(reinterpret_cast<const double2*>(p) + i2)
+               : "=d"(v.v[0]), "=d"(v.v[1])
+               : "l"(reinterpret_cast<const double2*>(p) + ip)
                : "memory");
   return v;
 }
-__device__ __forceinline__ void st2(double* p, long long i2, double2 v) { reinterpret_cast<double2*>(p)[i2] = v; }
+__device__ __forceinline__ Pack<float> ldp(const float* p, long long ip) {
+  Pack<float> v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.v[0]), "=f"(v.v[1]), "=f"(v.v[2]), "=f"(v.v[3])
+               : "l"(reinterpret_cast<const float4*>(p) + ip)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void stp(double* p, long long ip, const Pack<double>& v) {
+  reinterpret_cast<double2*>(p)[ip] = make_double2(v.v[0], v.v[1]);
+}
+__device__ __forceinline__ void stp(float* p, long long ip, const Pack<float>& v) {
+  reinterpret_cast<float4*>(p)[ip] = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+}
+template <typename T>
+__device__ __forceinline__ Pack<T> pack_fill(T c) {
+  Pack<T> v;
+#pragma unroll
+  for (int j = 0; j < Pack<T>::N; ++j) v.v[j] = c;
+  return v;
+}
+// double accumulation of a product of two T values (exact product for float)
+__device__ __forceinline__ double dacc(double a, double b, double acc) { return fma_rn(a, b, acc); }
+__device__ __forceinline__ double dacc(float a, float b, double acc) {
+  return fma_rn(static_cast<double>(a), static_cast<double>(b), acc);
+}
+
+// Elements are dealt to threads in 128-bit packs in a fixed grid-stride order; the tail (n mod pack) is taken by
+// thread 0 of CTA 0.  fp(ip) handles pack ip, f1(i) a single element.
+template <typename T, typename FP, typename F1>
+__device__ __forceinline__ void vec_loop(long long n, FP fp, F1 f1) {
+  // Two packs per thread and trip: twice the bytes in flight per thread (the order in which a thread visits its
+  // elements, hence every reduction, is unchanged).
+  constexpr int U = 2;
+  constexpr int PN = Pack<T>::N;
+  const long long np = n / PN;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long ip = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; ip < np; ip += U * stride) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (ip + u * stride < np) fp(ip + u * stride);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = np * PN; i < n; ++i) f1(i);
+}
 
 // CG start (ConjugateGradient.h:43-67): r = b - A x0 (q holds A x0 when there is a guess, else r = b),
 // p = D^-1 r, and the three reductions ||b||^2, ||r||^2, r.p in the same pass.
-__global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const VecArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const VecArgsT<T> a) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32 * 3];
   const bool guess = a.red.S->use_guess != 0;
   double v[3] = {0.0, 0.0, 0.0};
-  vec_loop(a.n,
-    [&](long long i2) {
-      const double2 b = ld2(a.b, i2), d = ld2(a.invdiag, i2);
-      double2 r = b;
-      if (guess) { const double2 q = ld2(a.q, i2); r.x = b.x - q.x; r.y = b.y - q.y; }
-      else st2(a.x, i2, make_double2(0.0, 0.0));  // solve() starts from x = 0 (IterativeSolverBase.h:402)
-      double2 p; p.x = d.x * r.x; p.y = d.y * r.y;
-      st2(a.r, i2, r); st2(a.p, i2, p);
-      v[0] = fma_rn(b.x, b.x, v[0]); v[0] = fma_rn(b.y, b.y, v[0]);
-      v[1] = fma_rn(r.x, r.x, v[1]); v[1] = fma_rn(r.y, r.y, v[1]);
-      v[2] = fma_rn(r.x, p.x, v[2]); v[2] = fma_rn(r.y, p.y, v[2]);
+  auto elem = [&](T b, T q, T d, T& r, T& p) {
+    r = guess ? b - q : b;
+    p = d * r;
+    v[0] = dacc(b, b, v[0]);
+    v[1] = dacc(r, r, v[1]);
+    v[2] = dacc(r, p, v[2]);
+  };
+  vec_loop<T>(a.n,
+    [&](long long ip) {
+      const Pack<T> b = ldp(a.b, ip), d = ldp(a.invdiag, ip);
+      Pack<T> q = pack_fill<T>(T(0)), r, p;
+      if (guess) q = ldp(a.q, ip);
+      else stp(a.x, ip, pack_fill<T>(T(0)));  // solve() starts from x = 0 (IterativeSolverBase.h:402)
+#pragma unroll
+      for (int j = 0; j < Pack<T>::N; ++j) elem(b.v[j], q.v[j], d.v[j], r.v[j], p.v[j]);
+      stp(a.r, ip, r); stp(a.p, ip, p);
     },
     [&](long long i) {
-      const double b = a.b[i];
-      const double r = guess ? b - a.q[i] : b;
-      if (!guess) a.x[i] = 0.0;
-      const double p = a.invdiag[i] * r;
+      T r, p;
+      elem(a.b[i], guess ? a.q[i] : T(0), a.invdiag[i], r, p);
+      if (!guess) a.x[i] = T(0);
       a.r[i] = r; a.p[i] = p;
-      v[0] = fma_rn(b, b, v[0]); v[1] = fma_rn(r, r, v[1]); v[2] = fma_rn(r, p, v[2]);
     });
   finish_reduction<3, kVecThreads>(a.red, v, scratch, a.history);
 }
@@ -844,63 +933,72 @@ __global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const VecArgs a) {
 // The solution update x += alpha p (:74) is DEFERRED to the direction pass, which reads p anyway: one vector read
 // less per iteration (12 instead of 13 vector passes of 8N bytes).  Same operations on the same operands, so x is
 // bit-identical to the immediate update.
-__device__ __forceinline__ void cg_update_body(const VecArgs& av, const double alpha, double (&v)[2]) {
-  struct { double* __restrict__ r; const double* __restrict__ q; const double* __restrict__ invdiag; } a = {av.r, av.q,
-                                                                                                        av.invdiag};
-  vec_loop(av.n,
-    [&](long long i2) {
-      double2 r = ld2(a.r, i2);
-      const double2 q = ld2(a.q, i2), d = ld2(a.invdiag, i2);
-      r.x = fma_rn(-alpha, q.x, r.x); r.y = fma_rn(-alpha, q.y, r.y);
-      st2(a.r, i2, r);
-      const double zx = d.x * r.x, zy = d.y * r.y;
-      v[0] = fma_rn(r.x, r.x, v[0]); v[0] = fma_rn(r.y, r.y, v[0]);
-      v[1] = fma_rn(r.x, zx, v[1]); v[1] = fma_rn(r.y, zy, v[1]);
+template <typename T>
+__device__ __forceinline__ void cg_update_body(const VecArgsT<T>& av, const T alpha, double (&v)[2]) {
+  struct { T* __restrict__ r; const T* __restrict__ q; const T* __restrict__ invdiag; } a = {av.r, av.q, av.invdiag};
+  auto elem = [&](T& r, T q, T d) {
+    r = fma_rn(-alpha, q, r);
+    const T z = d * r;
+    v[0] = dacc(r, r, v[0]);
+    v[1] = dacc(r, z, v[1]);
+  };
+  vec_loop<T>(av.n,
+    [&](long long ip) {
+      Pack<T> r = ldp(a.r, ip);
+      const Pack<T> q = ldp(a.q, ip), d = ldp(a.invdiag, ip);
+#pragma unroll
+      for (int j = 0; j < Pack<T>::N; ++j) elem(r.v[j], q.v[j], d.v[j]);
+      stp(a.r, ip, r);
     },
     [&](long long i) {
-      const double r = fma_rn(-alpha, a.q[i], a.r[i]);
+      T r = a.r[i];
+      elem(r, a.q[i], a.invdiag[i]);
       a.r[i] = r;
-      const double z = a.invdiag[i] * r;
-      v[0] = fma_rn(r, r, v[0]); v[1] = fma_rn(r, z, v[1]);
     });
 }
 
-__global__ void __launch_bounds__(kVecThreads) cg_update_kernel(const VecArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) cg_update_kernel(const VecArgsT<T> a) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32 * 2];
   if (gated_out(a.red.S, a.red.gate)) return;
   double v[2] = {0.0, 0.0};
-  cg_update_body(a, a.red.S->alpha, v);
+  cg_update_body<T>(a, static_cast<T>(a.red.S->alpha), v);
   finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
 }
 
 // CG :74 (deferred) and :81,:86: x += alpha p, then -- unless the loop has just stopped -- p = D^-1 r + beta p
-__device__ __forceinline__ void cg_direction_body(const VecArgs& av, const double alpha, const double beta,
+template <typename T>
+__device__ __forceinline__ void cg_direction_body(const VecArgsT<T>& av, const T alpha, const T beta,
                                                   const bool update_p) {
-  struct { double* __restrict__ x; double* __restrict__ p; const double* __restrict__ r;
-           const double* __restrict__ invdiag; } a = {av.x, av.p, av.r, av.invdiag};
+  struct { T* __restrict__ x; T* __restrict__ p; const T* __restrict__ r; const T* __restrict__ invdiag; } a = {
+      av.x, av.p, av.r, av.invdiag};
   if (update_p) {
-    vec_loop(av.n,
-      [&](long long i2) {
-        const double2 r = ld2(a.r, i2), d = ld2(a.invdiag, i2);
-        double2 p = ld2(a.p, i2), x = ld2(a.x, i2);
-        x.x = fma_rn(alpha, p.x, x.x); x.y = fma_rn(alpha, p.y, x.y);
-        p.x = fma_rn(beta, p.x, d.x * r.x); p.y = fma_rn(beta, p.y, d.y * r.y);
-        st2(a.x, i2, x); st2(a.p, i2, p);
+    vec_loop<T>(av.n,
+      [&](long long ip) {
+        const Pack<T> r = ldp(a.r, ip), d = ldp(a.invdiag, ip);
+        Pack<T> p = ldp(a.p, ip), x = ldp(a.x, ip);
+#pragma unroll
+        for (int j = 0; j < Pack<T>::N; ++j) {
+          x.v[j] = fma_rn(alpha, p.v[j], x.v[j]);
+          p.v[j] = fma_rn(beta, p.v[j], d.v[j] * r.v[j]);
+        }
+        stp(a.x, ip, x); stp(a.p, ip, p);
       },
       [&](long long i) {
-        const double p = a.p[i];
+        const T p = a.p[i];
         a.x[i] = fma_rn(alpha, p, a.x[i]);
         a.p[i] = fma_rn(beta, p, a.invdiag[i] * a.r[i]);
       });
   } else {
-    vec_loop(av.n,
-      [&](long long i2) {
-        const double2 p = ld2(a.p, i2);
-        double2 x = ld2(a.x, i2);
-        x.x = fma_rn(alpha, p.x, x.x); x.y = fma_rn(alpha, p.y, x.y);
-        st2(a.x, i2, x);
+    vec_loop<T>(av.n,
+      [&](long long ip) {
+        const Pack<T> p = ldp(a.p, ip);
+        Pack<T> x = ldp(a.x, ip);
+#pragma unroll
+        for (int j = 0; j < Pack<T>::N; ++j) x.v[j] = fma_rn(alpha, p.v[j], x.v[j]);
+        stp(a.x, ip, x);
       },
       [&](long long i) { a.x[i] = fma_rn(alpha, a.p[i], a.x[i]); });
   }
@@ -908,12 +1006,13 @@ __device__ __forceinline__ void cg_direction_body(const VecArgs& av, const doubl
 
 // Runs after every cg_update: applies the pending x update exactly once (n_update counts updates, n_xapplied the
 // ones already folded into x; launches that find nothing pending -- gated copies after the stop -- do nothing).
-__global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgs a, unsigned int* ticket) {
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgsT<T> a, unsigned int* ticket) {
   pdl_launch_dependents();
   pdl_wait();
   const Scalars* S = a.red.S;
   if (S->n_update == S->n_xapplied) return;
-  cg_direction_body(a, S->alpha, S->beta, S->stop == 0);
+  cg_direction_body<T>(a, static_cast<T>(S->alpha), static_cast<T>(S->beta), S->stop == 0);
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(ticket, 1u);
@@ -926,131 +1025,159 @@ __global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgs
 }
 
 // BiCGSTAB start (BiCGSTAB.h:42-46): r = b - A x0 (t holds A x0), r0 = r, ||b||^2, ||r||^2; v = p = 0 (:56)
-__global__ void __launch_bounds__(kVecThreads) bicg_init_kernel(const VecArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bicg_init_kernel(const VecArgsT<T> a) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32 * 2];
   const bool guess = a.red.S->use_guess != 0;
   double v[2] = {0.0, 0.0};
-  vec_loop(a.n,
-    [&](long long i2) {
-      const double2 b = ld2(a.b, i2);
-      double2 r = b;
-      if (guess) { const double2 t = ld2(a.t, i2); r.x = b.x - t.x; r.y = b.y - t.y; }
-      else st2(a.x, i2, make_double2(0.0, 0.0));
-      st2(a.r, i2, r); st2(a.r0, i2, r);
-      st2(a.q, i2, make_double2(0.0, 0.0)); st2(a.p, i2, make_double2(0.0, 0.0));
-      v[0] = fma_rn(b.x, b.x, v[0]); v[0] = fma_rn(b.y, b.y, v[0]);
-      v[1] = fma_rn(r.x, r.x, v[1]); v[1] = fma_rn(r.y, r.y, v[1]);
+  vec_loop<T>(a.n,
+    [&](long long ip) {
+      const Pack<T> b = ldp(a.b, ip);
+      Pack<T> r = b;
+      if (guess) {
+        const Pack<T> t = ldp(a.t, ip);
+#pragma unroll
+        for (int j = 0; j < Pack<T>::N; ++j) r.v[j] = b.v[j] - t.v[j];
+      } else {
+        stp(a.x, ip, pack_fill<T>(T(0)));
+      }
+      stp(a.r, ip, r); stp(a.r0, ip, r);
+      stp(a.q, ip, pack_fill<T>(T(0))); stp(a.p, ip, pack_fill<T>(T(0)));
+#pragma unroll
+      for (int j = 0; j < Pack<T>::N; ++j) { v[0] = dacc(b.v[j], b.v[j], v[0]); v[1] = dacc(r.v[j], r.v[j], v[1]); }
     },
     [&](long long i) {
-      const double b = a.b[i];
-      const double r = guess ? b - a.t[i] : b;
-      if (!guess) a.x[i] = 0.0;
-      a.r[i] = r; a.r0[i] = r; a.q[i] = 0.0; a.p[i] = 0.0;
-      v[0] = fma_rn(b, b, v[0]); v[1] = fma_rn(r, r, v[1]);
+      const T b = a.b[i];
+      const T r = guess ? b - a.t[i] : b;
+      if (!guess) a.x[i] = T(0);
+      a.r[i] = r; a.r0[i] = r; a.q[i] = T(0); a.p[i] = T(0);
+      v[0] = dacc(b, b, v[0]); v[1] = dacc(r, r, v[1]);
     });
   finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
 }
 
 // BiCGSTAB restart (:75-77): r = b - A x (t holds A x), r0 = r, ||r||^2
-__global__ void __launch_bounds__(kVecThreads) bicg_restart_kernel(const VecArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bicg_restart_kernel(const VecArgsT<T> a) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32];
   if (gated_out(a.red.S, a.red.gate)) return;
   double v[1] = {0.0};
-  vec_loop(a.n,
-    [&](long long i2) {
-      const double2 b = ld2(a.b, i2), t = ld2(a.t, i2);
-      double2 r; r.x = b.x - t.x; r.y = b.y - t.y;
-      st2(a.r, i2, r); st2(a.r0, i2, r);
-      v[0] = fma_rn(r.x, r.x, v[0]); v[0] = fma_rn(r.y, r.y, v[0]);
+  vec_loop<T>(a.n,
+    [&](long long ip) {
+      const Pack<T> b = ldp(a.b, ip), t = ldp(a.t, ip);
+      Pack<T> r;
+#pragma unroll
+      for (int j = 0; j < Pack<T>::N; ++j) { r.v[j] = b.v[j] - t.v[j]; v[0] = dacc(r.v[j], r.v[j], v[0]); }
+      stp(a.r, ip, r); stp(a.r0, ip, r);
     },
     [&](long long i) {
-      const double r = a.b[i] - a.t[i];
+      const T r = a.b[i] - a.t[i];
       a.r[i] = r; a.r0[i] = r;
-      v[0] = fma_rn(r, r, v[0]);
+      v[0] = dacc(r, r, v[0]);
     });
   finish_reduction<1, kVecThreads>(a.red, v, scratch, a.history);
 }
 
 // BiCGSTAB :82-85: beta = (rho/rho_old)(alpha/w); p = r + beta (p - w v); y = D^-1 p
-__global__ void __launch_bounds__(kVecThreads) bicg_p_kernel(const VecArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bicg_p_kernel(const VecArgsT<T> a) {
   pdl_launch_dependents();
   pdl_wait();
   if (gated_out(a.red.S, a.red.gate)) return;
   const Scalars* S = a.red.S;
-  const double beta = (S->rho / S->rho_old) * (S->alpha / S->w);
-  const double w = S->w;
-  vec_loop(a.n,
-    [&](long long i2) {
-      const double2 r = ld2(a.r, i2), vv = ld2(a.q, i2), d = ld2(a.invdiag, i2);
-      double2 p = ld2(a.p, i2);
-      p.x = fma_rn(beta, fma_rn(-w, vv.x, p.x), r.x); p.y = fma_rn(beta, fma_rn(-w, vv.y, p.y), r.y);
-      st2(a.p, i2, p);
-      st2(a.y, i2, make_double2(d.x * p.x, d.y * p.y));
+  // every factor is already a RealScalar value; the two quotients and the product are T operations (:82)
+  const T beta = (static_cast<T>(S->rho) / static_cast<T>(S->rho_old)) * (static_cast<T>(S->alpha) / static_cast<T>(S->w));
+  const T w = static_cast<T>(S->w);
+  vec_loop<T>(a.n,
+    [&](long long ip) {
+      const Pack<T> r = ldp(a.r, ip), vv = ldp(a.q, ip), d = ldp(a.invdiag, ip);
+      Pack<T> p = ldp(a.p, ip), y;
+#pragma unroll
+      for (int j = 0; j < Pack<T>::N; ++j) {
+        p.v[j] = fma_rn(beta, fma_rn(-w, vv.v[j], p.v[j]), r.v[j]);
+        y.v[j] = d.v[j] * p.v[j];
+      }
+      stp(a.p, ip, p);
+      stp(a.y, ip, y);
     },
     [&](long long i) {
-      const double p = fma_rn(beta, fma_rn(-w, a.q[i], a.p[i]), a.r[i]);
+      const T p = fma_rn(beta, fma_rn(-w, a.q[i], a.p[i]), a.r[i]);
       a.p[i] = p; a.y[i] = a.invdiag[i] * p;
     });
 }
 
 // BiCGSTAB :90-92: s = r - alpha v; z = D^-1 s
-__global__ void __launch_bounds__(kVecThreads) bicg_s_kernel(const VecArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bicg_s_kernel(const VecArgsT<T> a) {
   pdl_launch_dependents();
   pdl_wait();
   if (gated_out(a.red.S, a.red.gate)) return;
-  const double alpha = a.red.S->alpha;
-  vec_loop(a.n,
-    [&](long long i2) {
-      const double2 r = ld2(a.r, i2), vv = ld2(a.q, i2), d = ld2(a.invdiag, i2);
-      double2 s; s.x = fma_rn(-alpha, vv.x, r.x); s.y = fma_rn(-alpha, vv.y, r.y);
-      st2(a.s, i2, s);
-      st2(a.z, i2, make_double2(d.x * s.x, d.y * s.y));
+  const T alpha = static_cast<T>(a.red.S->alpha);
+  vec_loop<T>(a.n,
+    [&](long long ip) {
+      const Pack<T> r = ldp(a.r, ip), vv = ldp(a.q, ip), d = ldp(a.invdiag, ip);
+      Pack<T> s, z;
+#pragma unroll
+      for (int j = 0; j < Pack<T>::N; ++j) {
+        s.v[j] = fma_rn(-alpha, vv.v[j], r.v[j]);
+        z.v[j] = d.v[j] * s.v[j];
+      }
+      stp(a.s, ip, s);
+      stp(a.z, ip, z);
     },
     [&](long long i) {
-      const double s = fma_rn(-alpha, a.q[i], a.r[i]);
+      const T s = fma_rn(-alpha, a.q[i], a.r[i]);
       a.s[i] = s; a.z[i] = a.invdiag[i] * s;
     });
 }
 
 // BiCGSTAB :100-101 and the next loop head :67,:71: x += alpha y + w z; r = s - w t; ||r||^2; r0.r
-__global__ void __launch_bounds__(kVecThreads) bicg_update_kernel(const VecArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bicg_update_kernel(const VecArgsT<T> a) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32 * 2];
   if (gated_out(a.red.S, a.red.gate)) return;
-  const double alpha = a.red.S->alpha, w = a.red.S->w;
+  const T alpha = static_cast<T>(a.red.S->alpha), w = static_cast<T>(a.red.S->w);
   double v[2] = {0.0, 0.0};
-  vec_loop(a.n,
-    [&](long long i2) {
-      double2 x = ld2(a.x, i2);
-      const double2 y = ld2(a.y, i2), z = ld2(a.z, i2), s = ld2(a.s, i2), t = ld2(a.t, i2), r0 = ld2(a.r0, i2);
-      x.x = x.x + fma_rn(w, z.x, alpha * y.x); x.y = x.y + fma_rn(w, z.y, alpha * y.y);
-      double2 r; r.x = fma_rn(-w, t.x, s.x); r.y = fma_rn(-w, t.y, s.y);
-      st2(a.x, i2, x); st2(a.r, i2, r);
-      v[0] = fma_rn(r.x, r.x, v[0]); v[0] = fma_rn(r.y, r.y, v[0]);
-      v[1] = fma_rn(r0.x, r.x, v[1]); v[1] = fma_rn(r0.y, r.y, v[1]);
+  auto elem = [&](T& x, T y, T z, T s, T t, T r0, T& r) {
+    x = x + fma_rn(w, z, alpha * y);
+    r = fma_rn(-w, t, s);
+    v[0] = dacc(r, r, v[0]);
+    v[1] = dacc(r0, r, v[1]);
+  };
+  vec_loop<T>(a.n,
+    [&](long long ip) {
+      Pack<T> x = ldp(a.x, ip), r;
+      const Pack<T> y = ldp(a.y, ip), z = ldp(a.z, ip), s = ldp(a.s, ip), t = ldp(a.t, ip), r0 = ldp(a.r0, ip);
+#pragma unroll
+      for (int j = 0; j < Pack<T>::N; ++j) elem(x.v[j], y.v[j], z.v[j], s.v[j], t.v[j], r0.v[j], r.v[j]);
+      stp(a.x, ip, x); stp(a.r, ip, r);
     },
     [&](long long i) {
-      const double x = a.x[i] + fma_rn(w, a.z[i], alpha * a.y[i]);
-      const double r = fma_rn(-w, a.t[i], a.s[i]);
+      T x = a.x[i], r;
+      elem(x, a.y[i], a.z[i], a.s[i], a.t[i], a.r0[i], r);
       a.x[i] = x; a.r[i] = r;
-      v[0] = fma_rn(r, r, v[0]); v[1] = fma_rn(a.r0[i], r, v[1]);
     });
   finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
 }
 
-// x = 0 when ||b|| == 0 (ConjugateGradient.h:48, BiCGSTAB.h:49); otherwise nothing.
-__global__ void __launch_bounds__(kVecThreads) finalize_kernel(const VecArgs a) {
+// x = 0 when ||b|| == 0 (ConjugateGradient.h:48, BiCGSTAB.h:49); x = NaN when CG ran into a non-finite residual norm
+// with at least the iterations left that the reference needs to spread it over x (see kEpiCgInit); otherwise nothing.
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) finalize_kernel(const VecArgsT<T> a) {
   pdl_launch_dependents();
   pdl_wait();
-  if (!a.red.S->rhs_zero) return;
+  const bool zero = a.red.S->rhs_zero != 0, nan = a.red.S->numerical_issue == 2;
+  if (!zero && !nan) return;
+  const T fill = zero ? T(0) : static_cast<T>(__longlong_as_double(0x7ff8000000000000ll));
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
-    a.x[i] = 0.0;
+    a.x[i] = fill;
 }
 
 // Sets the WHILE condition from the control state (used after the init phase and by chunk boundaries).
@@ -1063,12 +1190,15 @@ __global__ void set_condition_kernel(const Scalars* S, unsigned long long handle
 // The whole loop of ConjugateGradient.h:69-88 in ONE cooperative kernel: the three passes of an iteration are phases
 // separated by grid-wide barriers instead of kernel boundaries, and the reductions ride on the barriers (the CTA
 // that arrives last folds the partials, all-reduces over ranks, runs the scalar epilogue, then releases everybody).
-// Same device functions, same arithmetic and the same reduction order as the three-kernel pipeline, so results are
-// bit-identical to the graph modes; what disappears is launch latency, which dominates when an iteration is tens of
-// microseconds (strong scaling over 8 GPUs, L2-sized problems).
+// Same device functions and the same arithmetic as the three-kernel pipeline; the vector phases run on this kernel's
+// grid, so the grouping of the partial sums (hence the last bits of the dot products) matches the graph modes only
+// while both grids cover the vector in one sweep (n/2 <= grid * 256); beyond that the two are equally deterministic
+// but not bit-identical to each other.  What disappears is launch latency, which dominates when an iteration is
+// tens of microseconds (strong scaling over 8 GPUs, L2-sized problems).
+template <typename T>
 struct CgPersistArgs {
-  SpmvArgs<double> sp;
-  VecArgs ve;
+  SpmvArgs<T> sp;
+  VecArgsT<T> ve;
   unsigned int* bar_count;
   unsigned int* bar_gen;
 };
@@ -1125,24 +1255,31 @@ __device__ __forceinline__ void grid_sync(const RedCtx& ctx, double* v, double* 
         timeline_mark(ctx.S, ctx.epilogue);
         run_epilogue(ctx, r, history);
       }
+      if (ctx.S->comm_error) ctx.S->stop = 1;
       __threadfence();
       st_release_gpu(bar_gen, gen + 1);
     }
   } else if (threadIdx.x == 0) {
-    while (ld_acquire_gpu(bar_gen) != gen + 1) __nanosleep(40);  // back off: 591 pollers share one L2 line
+    unsigned spins = 0;
+    const unsigned long long tw = globaltimer_ns();
+    while (ld_acquire_gpu(bar_gen) != gen + 1) {  // back off: 591 pollers share one L2 line
+      __nanosleep(40);
+      if (spin_expired(ctx.S, tw, spins)) break;
+    }
     __threadfence();
   }
   __syncthreads();
   ++gen;
 }
 
-__global__ void __launch_bounds__(kSpmvThreads, 1024 / kSpmvThreads) cg_persistent_kernel(const CgPersistArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(kSpmvThreads, 1024 / kSpmvThreads) cg_persistent_kernel(const CgPersistArgs<T> a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_bar[8];
   __shared__ double red_scratch[32 * 2];
-  __shared__ double long_scratch[32];
+  __shared__ T long_scratch[32];
   Scalars* S = a.sp.red.S;
-  SpmvCta<double> cx;
+  SpmvCta<T> cx;
   spmv_cta_init(a.sp, cx, smem, full_bar, long_scratch);
   unsigned gen = __ldcg(a.bar_gen);  // stable: only barriers of THIS kernel advance it, and nobody has arrived yet
   // every CTA must have read `gen` before anyone can release the first barrier: guaranteed, because a release needs
@@ -1164,13 +1301,13 @@ __global__ void __launch_bounds__(kSpmvThreads, 1024 / kSpmvThreads) cg_persiste
   // S changes only inside barrier epilogues, so after every barrier all CTAs read the same control state
   while (!__ldcg(&S->stop)) {
     if (!first) {
-      cg_direction_body(a.ve, __ldcg(&S->alpha), __ldcg(&S->beta), true);
+      cg_direction_body<T>(a.ve, static_cast<T>(__ldcg(&S->alpha)), static_cast<T>(__ldcg(&S->beta)), true);
       grid_sync<0, kSpmvThreads>(red_none, nullptr, red_scratch, a.ve.history, a.bar_count, a.bar_gen, gen);
     }
     first = false;
-    if (a.sp.halo.enabled) halo_push<double>(a.sp.halo, a.sp.red.comm, S, a.sp.x);
+    if (a.sp.halo.enabled) halo_push<T>(a.sp.halo, a.sp.red.comm, S, a.sp.x);
     double d0 = 0.0, d1 = 0.0;
-    spmv_tiles<double, 1, false>(a.sp, cx, d0, d1);
+    spmv_tiles<T, 1, false>(a.sp, cx, d0, d1);
     spmv_prefetch(a.sp, cx);  // the next product's first tiles fly during the two vector phases
     {
       double v[1] = {d0};
@@ -1178,12 +1315,12 @@ __global__ void __launch_bounds__(kSpmvThreads, 1024 / kSpmvThreads) cg_persiste
     }
     {
       double v[2] = {0.0, 0.0};
-      cg_update_body(a.ve, __ldcg(&S->alpha), v);
+      cg_update_body<T>(a.ve, static_cast<T>(__ldcg(&S->alpha)), v);
       grid_sync<2, kSpmvThreads>(red_upd, v, red_scratch, a.ve.history, a.bar_count, a.bar_gen, gen);
     }
   }
   if (!first) {  // the last iteration's x += alpha p is still owed (the loop stopped before its direction pass)
-    cg_direction_body(a.ve, __ldcg(&S->alpha), 0.0, false);
+    cg_direction_body<T>(a.ve, static_cast<T>(__ldcg(&S->alpha)), T(0), false);
     if (blockIdx.x == 0 && threadIdx.x == 0) S->n_xapplied = S->n_update;
   }
   if (pending) {  // tiles prefetched for a product that will not happen: wait until the copies have landed

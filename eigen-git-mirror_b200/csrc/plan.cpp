@@ -32,17 +32,28 @@ int canonicalise(int64_t rows, int64_t nnz, const int32_t* rowptr, const int32_t
     if (!inner_nnz) {  // already canonical
       std::memcpy(p.rowptr.data(), rowptr, sizeof(int32_t) * (rows + 1));
       if (p.rowptr[0] != 0) {  // a Map/Ref of an inner panel may start past 0: rebase
-        int32_t base = p.rowptr[0];
+        const int32_t base = p.rowptr[0];
+        const int64_t cnt = static_cast<int64_t>(p.rowptr[rows]) - base;  // entries actually referenced
+        if (base < 0 || cnt < 0) { err = "rowptr is not monotone"; return B200S_ERR_INVALID; }
         for (auto& v : p.rowptr) v -= base;
-        p.src.resize(nnz);
-        for (int64_t k = 0; k < nnz; ++k) p.src[k] = base + static_cast<int32_t>(k);
-        p.colidx.assign(colidx + base, colidx + base + nnz);
+        p.src.resize(cnt);
+        for (int64_t k = 0; k < cnt; ++k) p.src[k] = base + static_cast<int32_t>(k);
+        p.colidx.assign(colidx + base, colidx + base + cnt);
+        p.input_nnz = static_cast<int64_t>(base) + cnt;  // the caller's arrays are read up to slot base+cnt-1
+      } else if (rows > 0 && p.rowptr[rows] > nnz) {
+        err = "rowptr[rows] exceeds nnz";
+        return B200S_ERR_INVALID;
       }
       return 0;
     }
-    int64_t total = 0;
-    for (int64_t i = 0; i < rows; ++i) total += inner_nnz[i];
+    int64_t total = 0, span = 0;
+    for (int64_t i = 0; i < rows; ++i) {
+      if (inner_nnz[i] < 0) { err = "inner_nnz is negative"; return B200S_ERR_INVALID; }
+      total += inner_nnz[i];
+      span = std::max<int64_t>(span, row_end(i));
+    }
     if (total >= (int64_t(1) << 31)) { err = "nnz does not fit int32"; return B200S_ERR_UNSUPPORTED; }
+    p.input_nnz = span;  // one past the last slot any row references (the arrays have holes)
     p.src.resize(total);
     p.colidx.resize(total);
     int64_t o = 0;
@@ -59,6 +70,11 @@ int canonicalise(int64_t rows, int64_t nnz, const int32_t* rowptr, const int32_t
   // one triangle -> full symmetric
   const bool lower = (uplo == B200S_LOWER);
   std::vector<int64_t> n_lo(rows, 0), n_di(rows, 0), n_hi(rows, 0);
+  {
+    int64_t span = 0;
+    for (int64_t i = 0; i < rows; ++i) span = std::max<int64_t>(span, row_end(i));
+    p.input_nnz = span;
+  }
   for (int64_t i = 0; i < rows; ++i)
     for (int32_t k = rowptr[i]; k < row_end(i); ++k) {
       int64_t c = colidx[k];
@@ -188,7 +204,8 @@ int build_plan(const b200s_config& cfg, int64_t rows, int64_t cols, int64_t nnz,
   p.cols = cols;
   p.input_nnz = nnz;
   if (p.world == 1) {
-    if (rows != cols) { err = "solver matrices must be square (rows != cols)"; return B200S_ERR_INVALID; }
+    // rectangular matrices are fine for the product (SparseDenseProduct.h:26-72); the solvers insist on square ones
+    if (rows != cols && uplo != B200S_BOTH) { err = "a self-adjoint view needs a square matrix"; return B200S_ERR_INVALID; }
     p.row_starts = {0, rows};
   } else {
     if (!row_starts) { err = "row_starts is required when world > 1"; return B200S_ERR_INVALID; }

@@ -46,7 +46,7 @@ struct Plan {
   const int32_t* alias_colidx = nullptr;
   // src[k] = index into the caller's value array of local entry k; empty = identity.
   std::vector<int32_t> src;
-  int64_t input_nnz = 0;  // length of the caller's value array
+  int64_t input_nnz = 0;  // slots of the caller's value array that are read: one past the last referenced slot
   // Halo plan.
   std::vector<int64_t> ghost_cols;     // sorted global ids; local column of ghost g is rows + g
   std::vector<int64_t> recv_counts;    // [world] ghosts owned by each peer

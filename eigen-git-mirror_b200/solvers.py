@@ -24,7 +24,7 @@ Success, NumericalIssue, NoConvergence, InvalidInput = 0, 1, 2, 3
 IdentityPreconditioner, DiagonalPreconditioner = 0, 1
 
 SPMV_AUTO, SPMV_STAGED, SPMV_DIRECT = 0, 1, 2
-LOOP_AUTO, LOOP_WHILE_GRAPH, LOOP_CHUNKED_GRAPH, LOOP_STREAM = 0, 1, 2, 3
+LOOP_AUTO, LOOP_WHILE_GRAPH, LOOP_CHUNKED_GRAPH, LOOP_STREAM, LOOP_PERSISTENT = 0, 1, 2, 3, 4
 
 
 def device_count() -> int:
@@ -42,13 +42,27 @@ def _ptr(a) -> C.c_void_p:
     return C.c_void_p(int(a))
 
 
+def _index32(a, what: str) -> np.ndarray:
+    """The C ABI reads int32 indices through raw pointers: hand it nothing else (Eigen's default StorageIndex)."""
+    a = np.asarray(a)
+    if a.dtype == np.int32 and a.flags.c_contiguous:
+        return a
+    if a.size and (a.max() > np.iinfo(np.int32).max or a.min() < np.iinfo(np.int32).min):
+        raise ValueError(f"{what} does not fit int32 (StorageIndex = int)")
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
 def _as_csr(A) -> CsrMatrix:
     if isinstance(A, CsrMatrix):
-        return A
+        rp, ci = _index32(A.rowptr, "rowptr"), _index32(A.colidx, "colidx")
+        vals = np.ascontiguousarray(A.vals)
+        if rp is A.rowptr and ci is A.colidx and vals is A.vals:
+            return A
+        return CsrMatrix(A.rows, A.cols, rp, ci, vals, A.row0, A.name)
     if hasattr(A, "indptr"):  # scipy.sparse
         A = A.tocsr()
-        return CsrMatrix(A.shape[0], A.shape[1], np.ascontiguousarray(A.indptr, np.int32),
-                         np.ascontiguousarray(A.indices, np.int32), np.ascontiguousarray(A.data), 0)
+        return CsrMatrix(A.shape[0], A.shape[1], _index32(A.indptr, "rowptr"), _index32(A.indices, "colidx"),
+                         np.ascontiguousarray(A.data), 0)
     raise TypeError("expected a CsrMatrix or a scipy.sparse matrix")
 
 
@@ -91,11 +105,25 @@ class Communicator:
         return Communicator(dist.get_rank(group), dist.get_world_size(group), allgather, row_starts)
 
 
-def partition_rows(n: int, world: int, align: int = 1) -> np.ndarray:
-    """Contiguous, balanced row blocks; ``align`` keeps block edges on grid-plane boundaries."""
-    units = n // align
-    starts = [(units * r // world) * align for r in range(world)] + [n]
-    return np.asarray(starts, dtype=np.int64)
+def partition_rows(n: int, world: int, align: int = 1, rowptr=None, vector_bytes_per_row: int = 104) -> np.ndarray:
+    """Contiguous row blocks; ``align`` keeps block edges on grid-plane boundaries.
+
+    Without ``rowptr`` the blocks hold equal numbers of rows (right for stencils).  With the GLOBAL ``rowptr`` they
+    are balanced by the bytes one solver iteration streams per row -- 12 per stored entry plus
+    ``vector_bytes_per_row`` (CG: 13 vector passes of 8 bytes) -- which is what keeps ranks in step on matrices with
+    uneven row lengths (power-law)."""
+    if rowptr is None:
+        units = n // align
+        starts = [(units * r // world) * align for r in range(world)] + [n]
+        return np.asarray(starts, dtype=np.int64)
+    rp = np.asarray(rowptr, dtype=np.int64)
+    assert rp.shape[0] == n + 1
+    cost = 12 * (rp - rp[0]) + vector_bytes_per_row * np.arange(n + 1, dtype=np.int64)
+    targets = cost[-1] * np.arange(1, world, dtype=np.float64) / world
+    cuts = np.searchsorted(cost, targets, side="left")
+    cuts = (np.round(cuts / align).astype(np.int64) * align).clip(0, n)
+    starts = np.concatenate([[0], np.maximum.accumulate(cuts), [n]])
+    return starts.astype(np.int64)
 
 
 class _Handle:
@@ -210,6 +238,7 @@ class SparseOperator:
         return ms.value
 
     def invdiag(self) -> np.ndarray:
+        """DiagonalPreconditioner::m_invdiag of a double factorization."""
         d = np.empty(self._rows, dtype=np.float64)
         self._hd.check(self._hd.L.b200s_get_invdiag_f64(self._hd.h, _ptr(d)))
         return d
@@ -229,7 +258,7 @@ class _IterativeSolverBase(SparseOperator):
     def __init__(self, A=None, uplo: int = Lower | Upper, preconditioner: int = DiagonalPreconditioner,
                  comm: Optional[Communicator] = None, **cfg):
         self._precond = preconditioner
-        self._tolerance = float(np.finfo(np.float64).eps)  # :413
+        self._tolerance = -1.0                               # :413 -> NumTraits<Scalar>::epsilon(), resolved per dtype
         self._max_iterations = -1                            # :281-284 -> 2*cols
         self._iterations = 0
         self._error = 0.0
@@ -261,6 +290,8 @@ class _IterativeSolverBase(SparseOperator):
 
     # ---- parameters (:258-293) ----
     def tolerance(self):
+        if self._tolerance < 0:
+            return float(np.finfo(self._dtype if self._dtype is not None else np.float64).eps)
         return self._tolerance
 
     def setTolerance(self, tol):
@@ -293,31 +324,38 @@ class _IterativeSolverBase(SparseOperator):
     # ---- solves (:316-323, :333-404) ----
     def _solve_vector(self, b: np.ndarray, x: np.ndarray, use_guess: bool):
         it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
-        fn = self._hd.L.b200s_bicgstab_solve_f64 if self._bicg else self._hd.L.b200s_cg_solve_f64
-        self._hd.check(fn(self._hd.h, _ptr(b), _ptr(x), int(use_guess), self._tolerance, self.maxIterations(),
+        fn = getattr(self._hd.L, f"b200s_{'bicgstab' if self._bicg else 'cg'}_solve_{self._sfx()}")
+        self._hd.check(fn(self._hd.h, _ptr(b), _ptr(x), int(use_guess), self.tolerance(), self.maxIterations(),
                           C.byref(it), C.byref(err), C.byref(info)))
         return it.value, err.value, info.value
+
+    def _sfx(self):
+        return "f32" if self._dtype == np.float32 else "f64"
 
     def _solve(self, b, x0):
         if not self._is_initialized:
             raise AssertionError("solver is not initialized.")  # :337
-        b = np.asarray(b, dtype=np.float64)
+        dt = self._dtype if self._dtype is not None else np.float64
+        b = np.asarray(b, dtype=dt)
         if b.shape[0] != self._rows:
             raise AssertionError("solve(): invalid number of rows of the right hand side matrix b")
+        if x0 is not None and np.shape(x0) != b.shape:
+            raise AssertionError("solveWithGuess(): the guess must have the shape of the right hand side")  # :319
         if b.ndim == 1:
-            x = np.zeros(self._rows) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+            x = np.zeros(self._rows, dt) if x0 is None else np.array(x0, dtype=dt, copy=True)
             self._iterations, self._error, self._info = self._solve_vector(np.ascontiguousarray(b), x, x0 is not None)
             return x
         # multi-column right-hand side: sequential, info = worst, iterations / error = last column (:375-388)
-        X = np.zeros(b.shape, order="F") if x0 is None else np.array(x0, dtype=np.float64, order="F", copy=True)
+        X = np.zeros(b.shape, dt, order="F") if x0 is None else np.array(x0, dtype=dt, order="F", copy=True)
         global_info = Success
         for k in range(b.shape[1]):
             xk = np.ascontiguousarray(X[:, k])
             self._iterations, self._error, info = self._solve_vector(np.ascontiguousarray(b[:, k]), xk, x0 is not None)
             X[:, k] = xk
+            # IterativeSolverBase.h:355-358 / :383-386, literally: a later NoConvergence overwrites NumericalIssue
             if info == NumericalIssue:
                 global_info = NumericalIssue
-            elif info == NoConvergence and global_info != NumericalIssue:
+            elif info == NoConvergence:
                 global_info = NoConvergence
         self._info = global_info
         return X
@@ -331,8 +369,8 @@ class _IterativeSolverBase(SparseOperator):
     def solve_device(self, b_dev, x_dev, use_guess: bool = False):
         """Inputs resident in HBM (torch tensors / device addresses of this rank's rows)."""
         it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
-        fn = self._hd.L.b200s_bicgstab_solve_device_f64 if self._bicg else self._hd.L.b200s_cg_solve_device_f64
-        self._hd.check(fn(self._hd.h, _ptr(b_dev), _ptr(x_dev), int(use_guess), self._tolerance, self.maxIterations(),
+        fn = getattr(self._hd.L, f"b200s_{'bicgstab' if self._bicg else 'cg'}_solve_device_{self._sfx()}")
+        self._hd.check(fn(self._hd.h, _ptr(b_dev), _ptr(x_dev), int(use_guess), self.tolerance(), self.maxIterations(),
                           C.byref(it), C.byref(err), C.byref(info)))
         self._iterations, self._error, self._info = it.value, err.value, info.value
         return x_dev
@@ -357,12 +395,13 @@ class _IterativeSolverBase(SparseOperator):
 
 
 class ConjugateGradient(_IterativeSolverBase):
-    """ConjugateGradient<SparseMatrix<double,RowMajor>, UpLo, Preconditioner> (ConjugateGradient.h:157-225)."""
+    """ConjugateGradient<SparseMatrix<Scalar,RowMajor>, UpLo, Preconditioner> (ConjugateGradient.h:157-225); Scalar =
+    double or float follows the dtype of the matrix values given to compute()/factorize()."""
     _bicg = False
 
 
 class BiCGSTAB(_IterativeSolverBase):
-    """BiCGSTAB<SparseMatrix<double,RowMajor>, Preconditioner> (BiCGSTAB.h:157-208); the matrix is used as stored."""
+    """BiCGSTAB<SparseMatrix<Scalar,RowMajor>, Preconditioner> (BiCGSTAB.h:157-208); the matrix is used as stored."""
     _bicg = True
 
     def __init__(self, A=None, preconditioner: int = DiagonalPreconditioner, comm: Optional[Communicator] = None,

@@ -13,6 +13,14 @@
 //     KLUSupport/KLUSupport.h:60-115 wrapping klu_*;
 //   * _solve_vector_with_guess_impl (ConjugateGradient.h:197-221, BiCGSTAB.h:193-204) calls b200s_*_solve_f64 instead
 //     of internal::conjugate_gradient / internal::bicgstab.
+// Scalar = double or float (the reference's real instantiations, ConjugateGradient.h:157-160); complex does not compile.
+// b200/SparseOperator.h holds the SpMV-only drop-in (operator concept, doc/examples/matrixfree_cg.cpp:14-76).
+//
+// Row-partitioned use from C++ (one process per GPU): call setDistributed(rank, world, row_starts, allgather, ctx)
+// before compute(); compute() then takes THIS rank's row block as a rows_local x N row-major matrix with global column
+// indices, solve() takes this rank's block of b and returns an N-vector whose segment [row_starts[rank],
+// row_starts[rank+1]) holds this rank's block of x (the rest is zero).  `allgather` is only used during setup and for
+// the status exchange before a launch (MPI_Allgather, or any bootstrap the host has).
 // Header-only; needs Eigen on the include path and libb200sparse.so at link time.  There is no CPU fallback: with an
 // unsupported instantiation the code does not compile, without a B200 info() reports InvalidInput.
 #ifndef B200_ITERATIVE_SOLVERS_H
@@ -21,6 +29,7 @@
 #include <Eigen/IterativeLinearSolvers>
 #include <Eigen/SparseCore>
 
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -65,31 +74,77 @@ struct precond_id<Eigen::IdentityPreconditioner> {
   enum { supported = 1, value = B200S_PRECOND_IDENTITY };
 };
 
+// The C ABI entry points of one scalar type.
+template <typename S>
+struct abi {
+  enum { supported = 0 };
+};
+template <>
+struct abi<double> {
+  enum { supported = 1 };
+  static int factorize(b200s_handle* h, const double* v, int p) { return b200s_factorize_f64(h, v, p); }
+  static int spmv(b200s_handle* h, const double* x, double* y) { return b200s_spmv_f64(h, x, y); }
+  static int solve(b200s_handle* h, bool bicg, const double* b, double* x, int g, double tol, int64_t mi, int64_t* it,
+                   double* err, int* info) {
+    return bicg ? b200s_bicgstab_solve_f64(h, b, x, g, tol, mi, it, err, info)
+                : b200s_cg_solve_f64(h, b, x, g, tol, mi, it, err, info);
+  }
+};
+template <>
+struct abi<float> {
+  enum { supported = 1 };
+  static int factorize(b200s_handle* h, const float* v, int p) { return b200s_factorize_f32(h, v, p); }
+  static int spmv(b200s_handle* h, const float* x, float* y) { return b200s_spmv_f32(h, x, y); }
+  static int solve(b200s_handle* h, bool bicg, const float* b, float* x, int g, double tol, int64_t mi, int64_t* it,
+                   double* err, int* info) {
+    return bicg ? b200s_bicgstab_solve_f32(h, b, x, g, tol, mi, it, err, info)
+                : b200s_cg_solve_f32(h, b, x, g, tol, mi, it, err, info);
+  }
+};
+
 // Owns one b200s_handle and the host-side staging that turns an Eigen matrix view into the CSR arrays of the C ABI.
+template <typename Scalar>
 class DeviceSolver {
  public:
-  DeviceSolver() : m_handle(0) {}
-  ~DeviceSolver() {
-    if (m_handle) b200s_destroy(m_handle);
+  DeviceSolver() : m_handle(0), m_use_copy(false), m_rows(0), m_cols(0) {
+    std::memset(&m_cfg, 0, sizeof(m_cfg));
+    m_cfg.struct_size = sizeof(m_cfg);
+    m_cfg.device = -1;
+    m_cfg.world = 1;
   }
+  ~DeviceSolver() { reset(); }
   const std::string& lastError() const { return m_error; }
+  b200s_handle* handle() const { return m_handle; }
+  Eigen::Index rows() const { return m_rows; }
+  Eigen::Index cols() const { return m_cols; }
+  int world() const { return m_cfg.world; }
+  Eigen::Index rowStart() const { return m_cfg.world > 1 ? Eigen::Index(m_row_starts[m_cfg.rank]) : 0; }
+
+  // Must precede analyze(); a new configuration drops the device state.
+  void configure(const b200s_config& cfg, const int64_t* row_starts) {
+    reset();
+    m_cfg = cfg;
+    m_cfg.struct_size = sizeof(m_cfg);
+    if (m_cfg.world <= 0) m_cfg.world = 1;
+    m_row_starts.clear();
+    if (row_starts) m_row_starts.assign(row_starts, row_starts + m_cfg.world + 1);
+  }
 
   // `mat` is the solver's grabbed matrix (Ref<const MatrixType>).  `csr_uplo` is the triangle selection expressed for
   // the ROW-major reading of the arrays that are handed over.
   template <typename ActualMatrix>
   bool analyze(const ActualMatrix& mat, int uplo, bool need_transpose) {
     if (!ensure()) return false;
-    typedef typename ActualMatrix::Scalar Scalar;
     typedef typename ActualMatrix::StorageIndex StorageIndex;
     const bool row_major = ActualMatrix::IsRowMajor;
     m_use_copy = false;
     if (need_transpose && !row_major) {
-      // BiCGSTAB on a column-major matrix: the kernels need rows of A, the arrays hold rows of A^T.  One host-side
-      // conversion per compute() (the reference pays a serial scatter product per iteration instead,
+      // A general operator on a column-major matrix: the kernels need rows of A, the arrays hold rows of A^T.  One
+      // host-side conversion per compute() (the reference pays a serial scatter product per iteration instead,
       // SparseDenseProduct.h:85-107).
       m_rowmajor_copy = mat;
       m_use_copy = true;
-      return push_pattern(m_rowmajor_copy.rows(), m_rowmajor_copy.nonZeros(), m_rowmajor_copy.outerIndexPtr(),
+      return push_pattern(m_rowmajor_copy.rows(), m_rowmajor_copy.cols(), m_rowmajor_copy.outerIndexPtr(),
                           m_rowmajor_copy.innerIndexPtr(), m_rowmajor_copy.innerNonZeroPtr(), B200S_BOTH,
                           m_rowmajor_copy.outerIndexPtr()[m_rowmajor_copy.outerSize()]);
     }
@@ -98,20 +153,21 @@ class DeviceSolver {
     int csr_uplo = uplo;
     if (!row_major && uplo != B200S_BOTH) csr_uplo = (uplo == B200S_LOWER) ? B200S_UPPER : B200S_LOWER;
     const StorageIndex* outer = mat.outerIndexPtr();
-    const Eigen::Index span = mat.innerNonZeroPtr() ? Eigen::Index(outer[mat.outerSize()]) : Eigen::Index(mat.nonZeros());
-    (void)sizeof(Scalar);
-    return push_pattern(mat.outerSize(), mat.nonZeros(), outer, mat.innerIndexPtr(), mat.innerNonZeroPtr(), csr_uplo,
+    // one past the last slot the outer index references: equals nonZeros() for a compressed matrix that starts at
+    // slot 0, and stays correct for uncompressed storage (holes) and for a Map/Ref of an inner panel (outer[0] > 0)
+    const Eigen::Index span = Eigen::Index(outer[mat.outerSize()]);
+    return push_pattern(mat.outerSize(), mat.innerSize(), outer, mat.innerIndexPtr(), mat.innerNonZeroPtr(), csr_uplo,
                         span);
   }
 
   template <typename ActualMatrix>
   bool factorize(const ActualMatrix& mat, int precond) {
     if (!m_handle) return false;
-    const double* values = m_use_copy ? m_rowmajor_copy.valuePtr() : mat.valuePtr();
-    return check(b200s_factorize_f64(m_handle, values, precond));
+    const Scalar* values = m_use_copy ? m_rowmajor_copy.valuePtr() : mat.valuePtr();
+    return check(abi<Scalar>::factorize(m_handle, values, precond));
   }
 
-  bool solve(bool bicg, const double* b, double* x, bool use_guess, double tol, Eigen::Index max_iters,
+  bool solve(bool bicg, const Scalar* b, Scalar* x, bool use_guess, double tol, Eigen::Index max_iters,
              Eigen::Index& iters, double& error, Eigen::ComputationInfo& info) {
     if (!m_handle) {
       info = Eigen::InvalidInput;
@@ -120,9 +176,7 @@ class DeviceSolver {
     int64_t it = 0;
     int inf = 0;
     double err = 0;
-    int rc = bicg ? b200s_bicgstab_solve_f64(m_handle, b, x, use_guess ? 1 : 0, tol, max_iters, &it, &err, &inf)
-                  : b200s_cg_solve_f64(m_handle, b, x, use_guess ? 1 : 0, tol, max_iters, &it, &err, &inf);
-    if (!check(rc)) {
+    if (!check(abi<Scalar>::solve(m_handle, bicg, b, x, use_guess ? 1 : 0, tol, max_iters, &it, &err, &inf))) {
       info = Eigen::InvalidInput;
       return false;
     }
@@ -132,10 +186,20 @@ class DeviceSolver {
     return true;
   }
 
+  // y = A x through b200s_spmv_* (x: cols() entries on one GPU, this rank's rows otherwise; y: this rank's rows)
+  bool multiply(const Scalar* x, Scalar* y) {
+    if (!m_handle) return false;
+    return check(abi<Scalar>::spmv(m_handle, x, y));
+  }
+
  private:
+  void reset() {
+    if (m_handle) b200s_destroy(m_handle);
+    m_handle = 0;
+  }
   bool ensure() {
     if (m_handle) return true;
-    int rc = b200s_create(0, &m_handle);
+    int rc = b200s_create(&m_cfg, &m_handle);
     if (rc != B200S_OK) {
       m_error = b200s_last_error(0);
       m_handle = 0;
@@ -149,8 +213,8 @@ class DeviceSolver {
     return false;
   }
   template <typename StorageIndex>
-  bool push_pattern(Eigen::Index outer_size, Eigen::Index /*nnz*/, const StorageIndex* outer, const StorageIndex* inner,
-                    const StorageIndex* inner_nnz, int uplo, Eigen::Index span) {
+  bool push_pattern(Eigen::Index outer_size, Eigen::Index inner_size, const StorageIndex* outer,
+                    const StorageIndex* inner, const StorageIndex* inner_nnz, int uplo, Eigen::Index span) {
     // The C ABI speaks int32 (Eigen's default StorageIndex); wider index types are narrowed once per analyzePattern.
     const int32_t *o = 0, *i = 0, *z = 0;
     if (sizeof(StorageIndex) == sizeof(int32_t)) {
@@ -167,16 +231,44 @@ class DeviceSolver {
         z = m_innernnz32.data();
       }
     }
+    m_rows = outer_size;
+    m_cols = inner_size;
     // `span` = one past the last stored slot: for uncompressed matrices the value/index arrays have holes
-    return check(b200s_analyze_pattern(m_handle, outer_size, outer_size, span, o, i, z, uplo, 0));
+    return check(b200s_analyze_pattern(m_handle, outer_size, inner_size, span, o, i, z, uplo,
+                                       m_cfg.world > 1 ? m_row_starts.data() : 0));
   }
 
   b200s_handle* m_handle;
+  b200s_config m_cfg;
+  std::vector<int64_t> m_row_starts;
   std::string m_error;
   bool m_use_copy;
-  Eigen::SparseMatrix<double, Eigen::RowMajor, int> m_rowmajor_copy;
+  Eigen::Index m_rows, m_cols;
+  Eigen::SparseMatrix<Scalar, Eigen::RowMajor, int> m_rowmajor_copy;
   std::vector<int32_t> m_outer32, m_inner32, m_innernnz32;
 };
+
+// Shared by both solver classes: contiguous staging of b / x, the single-GPU and the row-partitioned calling shapes.
+template <typename Scalar, typename Rhs, typename Dest>
+void solve_vector(DeviceSolver<Scalar>& dev, bool bicg, const Rhs& b, Dest& x, double tol, Eigen::Index max_iters,
+                  Eigen::Index& iters, double& error, Eigen::ComputationInfo& info) {
+  typedef Eigen::Matrix<Scalar, Eigen::Dynamic, 1> Vec;
+  Vec bb = b;  // contiguous staging (b, x may be strided blocks or expressions)
+  if (dev.world() > 1) {
+    // x is an N-vector (the base class sizes it by cols()); this rank works on its own segment
+    Vec xx = x.segment(dev.rowStart(), dev.rows());
+    const bool guess = (xx.array() != Scalar(0)).any();
+    dev.solve(bicg, bb.data(), xx.data(), guess, tol, max_iters, iters, error, info);
+    x.setZero();
+    x.segment(dev.rowStart(), dev.rows()) = xx;
+    return;
+  }
+  Vec xx = x;
+  // solve() hands over x = 0 (IterativeSolverBase.h:402): skip the initial A*x0 product then, as r0 = b exactly
+  const bool guess = (xx.array() != Scalar(0)).any();
+  dev.solve(bicg, bb.data(), xx.data(), guess, tol, max_iters, iters, error, info);
+  x = xx;
+}
 
 }  // namespace detail
 
@@ -197,7 +289,7 @@ class ConjugateGradient : public Eigen::IterativeSolverBase<ConjugateGradient<Ma
   typedef Preconditioner_ Preconditioner;
   enum { UpLo = UpLo_ };
 
-  EIGEN_STATIC_ASSERT((Eigen::internal::is_same<Scalar, double>::value), THIS_TYPE_IS_NOT_SUPPORTED)
+  EIGEN_STATIC_ASSERT(detail::abi<Scalar>::supported, THIS_TYPE_IS_NOT_SUPPORTED)
   EIGEN_STATIC_ASSERT(detail::precond_id<Preconditioner>::supported, THIS_TYPE_IS_NOT_SUPPORTED)
 
   ConjugateGradient() : Base() {}
@@ -206,6 +298,20 @@ class ConjugateGradient : public Eigen::IterativeSolverBase<ConjugateGradient<Ma
   template <typename MatrixDerived>
   explicit ConjugateGradient(const Eigen::EigenBase<MatrixDerived>& A) : Base() {
     compute(A.derived());
+  }
+
+  /** Row-partitioned run, one process per GPU (see the file header).  Call before compute(). */
+  ConjugateGradient& setDistributed(int rank, int world, const int64_t* row_starts, b200s_allgather_fn allgather,
+                                    void* allgather_ctx, int device = -1) {
+    b200s_config cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.device = device;
+    cfg.rank = rank;
+    cfg.world = world;
+    cfg.allgather = allgather;
+    cfg.allgather_ctx = allgather_ctx;
+    m_dev.configure(cfg, row_starts);
+    return *this;
   }
 
   template <typename MatrixDerived>
@@ -232,20 +338,19 @@ class ConjugateGradient : public Eigen::IterativeSolverBase<ConjugateGradient<Ma
   /** \internal replaces ConjugateGradient.h:197-221 */
   template <typename Rhs, typename Dest>
   void _solve_vector_with_guess_impl(const Rhs& b, Dest& x) const {
-    Eigen::Matrix<double, Eigen::Dynamic, 1> bb = b, xx = x;  // contiguous staging (b, x may be strided blocks)
     m_iterations = Base::maxIterations();
     m_error = Base::m_tolerance;
-    // solve() hands over x = 0 (IterativeSolverBase.h:402): skip the initial A*x0 product then, as r0 = b exactly
-    const bool guess = (xx.array() != 0.0).any();
-    m_dev.solve(false, bb.data(), xx.data(), guess, Base::m_tolerance, Base::maxIterations(), m_iterations, m_error,
-                m_info);
-    x = xx;
+    double err = static_cast<double>(m_error);
+    detail::solve_vector<Scalar>(m_dev, false, b, x, static_cast<double>(Base::m_tolerance), Base::maxIterations(),
+                                 m_iterations, err, m_info);
+    m_error = static_cast<RealScalar>(err);
   }
 
   const std::string& lastError() const { return m_dev.lastError(); }
+  b200s_handle* handle() const { return m_dev.handle(); }
 
  protected:
-  mutable detail::DeviceSolver m_dev;
+  mutable detail::DeviceSolver<Scalar> m_dev;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -264,13 +369,27 @@ class BiCGSTAB : public Eigen::IterativeSolverBase<BiCGSTAB<MatrixType_, Precond
   typedef typename MatrixType::RealScalar RealScalar;
   typedef Preconditioner_ Preconditioner;
 
-  EIGEN_STATIC_ASSERT((Eigen::internal::is_same<Scalar, double>::value), THIS_TYPE_IS_NOT_SUPPORTED)
+  EIGEN_STATIC_ASSERT(detail::abi<Scalar>::supported, THIS_TYPE_IS_NOT_SUPPORTED)
   EIGEN_STATIC_ASSERT(detail::precond_id<Preconditioner>::supported, THIS_TYPE_IS_NOT_SUPPORTED)
 
   BiCGSTAB() : Base() {}
   template <typename MatrixDerived>
   explicit BiCGSTAB(const Eigen::EigenBase<MatrixDerived>& A) : Base() {
     compute(A.derived());
+  }
+
+  /** Row-partitioned run, one process per GPU (see the file header).  Call before compute(). */
+  BiCGSTAB& setDistributed(int rank, int world, const int64_t* row_starts, b200s_allgather_fn allgather,
+                           void* allgather_ctx, int device = -1) {
+    b200s_config cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.device = device;
+    cfg.rank = rank;
+    cfg.world = world;
+    cfg.allgather = allgather;
+    cfg.allgather_ctx = allgather_ctx;
+    m_dev.configure(cfg, row_starts);
+    return *this;
   }
 
   template <typename MatrixDerived>
@@ -299,20 +418,19 @@ class BiCGSTAB : public Eigen::IterativeSolverBase<BiCGSTAB<MatrixType_, Precond
   /** \internal replaces BiCGSTAB.h:193-204 */
   template <typename Rhs, typename Dest>
   void _solve_vector_with_guess_impl(const Rhs& b, Dest& x) const {
-    Eigen::Matrix<double, Eigen::Dynamic, 1> bb = b, xx = x;
     m_iterations = Base::maxIterations();
     m_error = Base::m_tolerance;
-    // solve() hands over x = 0 (IterativeSolverBase.h:402): skip the initial A*x0 product then, as r0 = b exactly
-    const bool guess = (xx.array() != 0.0).any();
-    m_dev.solve(true, bb.data(), xx.data(), guess, Base::m_tolerance, Base::maxIterations(), m_iterations, m_error,
-                m_info);
-    x = xx;
+    double err = static_cast<double>(m_error);
+    detail::solve_vector<Scalar>(m_dev, true, b, x, static_cast<double>(Base::m_tolerance), Base::maxIterations(),
+                                 m_iterations, err, m_info);
+    m_error = static_cast<RealScalar>(err);
   }
 
   const std::string& lastError() const { return m_dev.lastError(); }
+  b200s_handle* handle() const { return m_dev.handle(); }
 
  protected:
-  mutable detail::DeviceSolver m_dev;
+  mutable detail::DeviceSolver<Scalar> m_dev;
 };
 
 }  // namespace b200

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define B200S_VERSION 100
+#define B200S_VERSION 200
 
 typedef struct b200s_handle b200s_handle;
 
@@ -44,7 +44,7 @@ typedef enum {
   B200S_ERR_NO_DEVICE = -2, /* no CUDA device of compute capability 10.x: the product has no CPU path */
   B200S_ERR_CUDA = -3,      /* a CUDA runtime call failed; text in b200s_last_error */
   B200S_ERR_ALLOC = -4,
-  B200S_ERR_COMM = -5,      /* multi-GPU bootstrap failed */
+  B200S_ERR_COMM = -5,      /* multi-GPU bootstrap failed, a peer failed before a launch, or a device-side wait expired */
   B200S_ERR_UNSUPPORTED = -6
 } b200s_status;
 
@@ -99,6 +99,9 @@ typedef struct {
   int64_t last_iterations;
   int64_t last_spmv_count;          /* SpMV launches inside the last solve */
   int64_t device_bytes;             /* device memory held by the handle */
+  int64_t last_restarts;            /* BiCGSTAB: re-orthogonalisation restarts taken by the last solve (BiCGSTAB.h:72-81) */
+  int32_t last_nonfinite;           /* CG: the last solve stopped on a non-finite residual norm (outputs as the reference's) */
+  int32_t last_comm_error;          /* a bounded device-side wait on a peer expired during the last call */
 } b200s_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------ */
@@ -111,6 +114,8 @@ const char* b200s_last_error(const b200s_handle* h /* NULL: error of the last fa
 /* ---- setup: IterativeSolverBase::analyzePattern / factorize / compute (IterativeSolverBase.h:196-247) ----------
  * analyze_pattern takes THIS RANK's row block [row_starts[rank], row_starts[rank+1]) of a square `cols` x `cols`
  * matrix in CSR with GLOBAL column indices (world == 1: the whole matrix, row_starts may be NULL).
+ *   nnz       : number of slots in colidx / values, i.e. at least one past the last slot rowptr references
+ *               (rowptr[rows] for compressed storage, also when rowptr[0] > 0 as for a Map of an inner panel).
  *   inner_nnz : NULL for a compressed matrix, else Eigen's innerNonZeroPtr (SparseMatrix.h:176-183): row i holds
  *               entries [rowptr[i], rowptr[i]+inner_nnz[i]).
  *   uplo      : which stored triangle(s) define the operator.  LOWER / UPPER read one triangle and imply its mirror
@@ -139,9 +144,17 @@ int b200s_spmv_device_f32(b200s_handle* h, const float* x_dev, float* y_dev, int
  * holds the initial guess (solveWithGuess, :316-323).  tol < 0 -> machine epsilon (:413); max_iters < 0 -> 2*cols
  * (:281-284).  Outputs follow the reference exactly, including: CG counts completed iterations only
  * (ConjugateGradient.h:77-79,87); ||b|| == 0 gives x = 0 with iters = 0 / error = 0 for CG but iters = max_iters /
- * error = tol for BiCGSTAB (BiCGSTAB.h:47-51); info = error <= tol ? Success : NoConvergence; NumericalIssue if a
- * non-finite scalar appeared.  The whole iteration runs on the device (CUDA graph, on-device convergence test);
- * the host blocks until it is finished. */
+ * error = tol for BiCGSTAB (BiCGSTAB.h:47-51); info = error <= tol ? Success : NoConvergence.  A non-finite residual
+ * norm: the reference's CG loop spins on NaNs until max_iters and returns NoConvergence, iters = max_iters,
+ * error = NaN, x = NaN; this library stops at once and REPORTS those same outputs (b200s_stats.last_nonfinite says
+ * that it happened); BiCGSTAB leaves its loop on a NaN norm exactly as the reference does (BiCGSTAB.h:67).
+ * The whole iteration runs on the device (CUDA graph, on-device convergence test); the host blocks until it is
+ * finished.  The _f32 variants are the float instantiations (ConjugateGradient<SparseMatrix<float>>, ...): vectors,
+ * elementwise arithmetic and the scalar recurrences in float, dot products accumulated in double and rounded once;
+ * tol < 0 -> FLT_EPSILON.  They need factorize_f32.
+ * Row-partitioned runs (world > 1): every rank must make the same call; ranks exchange their status through the
+ * config's allgather before anything that waits on a peer is launched, and every device-side wait on a peer is
+ * bounded (B200S_COMM_TIMEOUT_MS, default 20000): a dead or diverged rank yields B200S_ERR_COMM, not a hang. */
 int b200s_cg_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
                        int64_t* iters_out, double* error_out, int* info_out);
 int b200s_bicgstab_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol,
@@ -149,6 +162,14 @@ int b200s_bicgstab_solve_f64(b200s_handle* h, const double* b, double* x, int us
 int b200s_cg_solve_device_f64(b200s_handle* h, const double* b_dev, double* x_dev, int use_guess, double tol,
                               int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
 int b200s_bicgstab_solve_device_f64(b200s_handle* h, const double* b_dev, double* x_dev, int use_guess, double tol,
+                                    int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
+int b200s_cg_solve_f32(b200s_handle* h, const float* b, float* x, int use_guess, double tol, int64_t max_iters,
+                       int64_t* iters_out, double* error_out, int* info_out);
+int b200s_bicgstab_solve_f32(b200s_handle* h, const float* b, float* x, int use_guess, double tol,
+                             int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
+int b200s_cg_solve_device_f32(b200s_handle* h, const float* b_dev, float* x_dev, int use_guess, double tol,
+                              int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
+int b200s_bicgstab_solve_device_f32(b200s_handle* h, const float* b_dev, float* x_dev, int use_guess, double tol,
                                     int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
 
 /* ---- introspection --------------------------------------------------------------------------------------------- */
@@ -184,6 +205,11 @@ int64_t b200s_plan_probe(const b200s_config* cfg, int64_t rows, int64_t cols, in
 int64_t b200s_plan_probe_csr(int64_t rows, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
                              const int32_t* inner_nnz, int uplo, int32_t* out_rowptr, int32_t* out_colidx,
                              int32_t* out_src, int64_t cap);
+
+/* Number of leading slots of the caller's value array that factorize will read for this pattern (one past the last
+ * slot any row references), or a negative status.  GPU-free. */
+int64_t b200s_plan_probe_span(int64_t rows, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                              const int32_t* inner_nnz, int uplo);
 
 #ifdef __cplusplus
 }

@@ -129,6 +129,11 @@ class Port:
         return self._solve(getattr(self.lib, f"oracle_bicgstab_{self._sfx(A.vals)}"), A, b, x0, tol, max_iters,
                            (precond, lanes))
 
+    @property
+    def last_restarts(self) -> int:
+        """Restarts (BiCGSTAB.h:72-81) taken by the last bicgstab() call of this port."""
+        return int(C.c_int64.in_dll(self.lib, "oracle_last_restarts").value)
+
     def true_residual(self, A, x, b):
         return self.lib.oracle_true_residual_f64(A.rows, A.rowptr, A.colidx, A.vals.astype(np.float64),
                                                  np.ascontiguousarray(x, np.float64),

@@ -15,6 +15,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* How often the last oracle_bicgstab_* call took the re-orthogonalisation branch (BiCGSTAB.h:72-81); the reference
+ * keeps this count in a local variable, tests need it to know that a case really exercises the branch. */
+int64_t oracle_last_restarts = 0;
+
 #define REAL double
 #define FMA fma
 #define SQRT sqrt

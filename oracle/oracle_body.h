@@ -224,6 +224,7 @@ void NAME(oracle_bicgstab)(int64_t n, const int32_t* rowptr, const int32_t* coli
 
   int64_t it = max_iters;
   REAL err = tol;
+  oracle_last_restarts = 0;
   NAME(oracle_spmv)(n, rowptr, colidx, vals, x, t); /* :42 r = rhs - mat*x */
   for (int64_t i = 0; i < n; ++i) r[i] = b[i] - t[i];
   memcpy(r0, r, sizeof(REAL) * (size_t)n);
@@ -248,6 +249,7 @@ void NAME(oracle_bicgstab)(int64_t n, const int32_t* rowptr, const int32_t* coli
         memcpy(r0, r, sizeof(REAL) * (size_t)n);
         rho = r0_sqnorm = NAME(oracle_dot)(r, r, n, lanes);
         if (restarts++ == 0) i_it = 0;
+        oracle_last_restarts = restarts;
       }
       REAL beta = (rho / rho_old) * (alpha / w); /* :82 */
       for (int64_t i = 0; i < n; ++i) p[i] = FMA(beta, FMA(-w, v[i], p[i]), r[i]); /* :83 */

@@ -13,11 +13,29 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100) device; run with `-m gpu` on the GPU box")
 
 
+class _Files:
+    """Several .npz files behind one mapping (keys are disjoint by construction)."""
+
+    def __init__(self, paths):
+        self.files = [np.load(p) for p in paths]
+        self.where = {k: f for f in self.files for k in f.keys()}
+
+    def keys(self):
+        return self.where.keys()
+
+    def __contains__(self, k):
+        return k in self.where
+
+    def __getitem__(self, k):
+        return self.where[k][k]
+
+
 class Golden:
-    """tests/golden/golden_v1.npz: outputs of the unmodified reference (see tests/golden/make_golden.py)."""
+    """tests/golden/golden_v1.npz + golden_v2.npz: outputs of the unmodified reference (see tests/golden/make_golden.py
+    and make_golden_v2.py)."""
 
     def __init__(self):
-        self.z = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+        self.z = _Files([os.path.join(ROOT, "tests", "golden", f) for f in ("golden_v1.npz", "golden_v2.npz")])
         self.keys = list(self.z.keys())
 
     def cases(self, prefix):
@@ -39,6 +57,27 @@ class Golden:
         key = str(self.get(case, "matrix"))
         g = lambda n: self.z[f"{key}/{n}"]
         return CsrMatrix(int(g("rows")), int(g("cols")), g("rowptr"), g("colidx"), g("vals"), 0, key)
+
+
+class Fullsize:
+    """tests/golden/fullsize_v1.npz: the unmodified reference on BASELINE.json's own configurations at full size
+    (tests/golden/make_fullsize.py): iterations, error(), ||x|| and 4,096 sampled entries of x, for the converged
+    solve and for the fixed-k trajectories."""
+
+    def __init__(self):
+        self.z = np.load(os.path.join(ROOT, "tests", "golden", "fullsize_v1.npz"))
+
+    def get(self, case, name):
+        v = self.z[f"{case}/{name}"]
+        return v.item() if v.ndim == 0 else v
+
+    def has(self, case, name):
+        return f"{case}/{name}" in self.z
+
+
+@pytest.fixture(scope="session")
+def fullsize():
+    return Fullsize()
 
 
 _golden = None

@@ -4,8 +4,16 @@ mode "plan" (CPU, gloo): builds the row-block plan through the GPU-free probe, p
 prescribes with torch.distributed, multiplies the local block with numpy and checks it against the oracle's global
 SpMV -- i.e. partition + ghost numbering + send lists are exactly what a correct distributed product needs.
 
-mode "gpu" (one process per GPU): SpMV, CG and BiCGSTAB through the C ABI on the partitioned problem; rank 0 gathers
-the pieces and compares with the oracle run on the whole problem.
+mode "gpu" (one process per GPU): SpMV, CG and BiCGSTAB through the C ABI on the partitioned problem (a few dozen SpMV
+tiles per rank, interior and boundary); every rank gathers the pieces and compares with the oracle run on the whole
+problem.
+
+mode "fullsize" (one process per GPU): BASELINE.json's configurations at full size -- name is cg_256, bicg_256 or
+cg_512 -- row-partitioned over the visible GPUs and compared with the reference fixtures of
+tests/golden/fullsize_v1.npz (tests/golden/make_fullsize.py) exactly as tests/test_gpu_fullsize.py does on one GPU.
+
+mode "deadpeer" (one process per GPU): rank 1 never calls solve(); the others must come back with B200S_ERR_COMM
+(status exchange before the launch), not hang.
 """
 import os
 import sys
@@ -16,16 +24,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def make(name):
+def make(name, big=False):
     from eigen_git_mirror_b200 import workloads as wl
+    n = 48 if big else 12
     if name == "poisson3d":
-        return wl.poisson3d(12), 144
+        return wl.poisson3d(n), n * n
     if name == "convdiff3d":
-        return wl.convdiff3d(12), 144
+        return wl.convdiff3d(n), n * n
     if name == "varcoef3d":
-        return wl.varcoef3d(10), 1
+        return wl.varcoef3d(40 if big else 10), 1
     if name == "powerlaw":
-        A = wl.powerlaw(1500, 6, seed=5)
+        A = wl.powerlaw(60000 if big else 1500, 6, seed=5)
         # make it diagonally dominant so that CG/BiCGSTAB behave: A <- A + A^T + 40 I
         S = A.to_scipy()
         import scipy.sparse as sp
@@ -65,8 +74,11 @@ def main():
     if mode == "gpu":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group(backend="gloo")
-    A, align = make(name)
-    starts = egm.partition_rows(A.rows, world, align=align)
+    if mode == "fullsize":
+        return fullsize(name, rank, world, dist, egm, wl)
+    A, align = make(name, big=(mode != "plan"))
+    # stencils: plane-aligned equal blocks; irregular rows: blocks balanced by the bytes an iteration streams
+    starts = egm.partition_rows(A.rows, world, align=align, rowptr=(A.rowptr if name == "powerlaw" else None))
     r0, r1 = int(starts[rank]), int(starts[rank + 1])
     Ab = block_of(A, r0, r1)
     comm = egm.Communicator.from_torch(starts)
@@ -101,6 +113,20 @@ def main():
             nb = (rank > 0) + (rank < world - 1)
             assert len(ext) == 144 * nb and v.stats["tiles_boundary"] <= 2 * nb + 1
         print(f"rank {rank}: plan ok, ghosts {len(ext)}, send {len(v.send_rows)}")
+    elif mode == "deadpeer":
+        s = egm.ConjugateGradient(Ab, comm=comm)
+        b = np.asarray(A.to_scipy() @ wl.random_vector(A.rows, 12345))
+        if rank == 1:
+            # this rank "fails on the host": it reports a non-zero status instead of launching
+            comm._allgather((-3).to_bytes(8, "little", signed=True))
+            print(f"rank {rank}: deadpeer ok (played dead)")
+        else:
+            try:
+                s.solve(b[r0:r1])
+                raise SystemExit("solve() returned although a peer never launched")
+            except egm.B200Error as e:
+                assert e.status == -5 and "rank 1 failed before the launch" in str(e), str(e)
+                print(f"rank {rank}: deadpeer ok ({e})")
     else:
         # ---- SpMV ----
         op = egm.SparseOperator(Ab, comm=comm)
@@ -141,6 +167,55 @@ def main():
         print(f"rank {rank}: gpu ok ({name}) {msg}; bicgstab iters {s2.iterations()} rel {rel:.2e}; "
               f"ghosts {op.stats()['ghosts']}")
         op.close(); s2.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def fullsize(name, rank, world, dist, egm, wl):
+    """BASELINE configs[1], [2], [4] row-partitioned over `world` GPUs against the reference fixtures."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    from conftest import Fullsize
+    from test_gpu_fullsize import KS, TOL, assert_close_to_reference, check_against_reference
+    fx = Fullsize()
+    n = 512 if name.endswith("512") else 256
+    bicg = name.startswith("bicg")
+    N = n ** 3
+    starts = egm.partition_rows(N, world, align=n * n)
+    r0, r1 = int(starts[rank]), int(starts[rank + 1])
+    A = (wl.convdiff3d if bicg else wl.poisson3d)(n, rows=(r0, r1))
+    x_true = wl.random_vector(N, 12345)
+    b = np.asarray(A.to_scipy() @ x_true)
+    del x_true
+    comm = egm.Communicator.from_torch(starts)
+    s = (egm.BiCGSTAB if bicg else egm.ConjugateGradient)(A, comm=comm)
+    s.setTolerance(TOL)
+
+    def reduce_parts(p):
+        t = torch.tensor(p, dtype=torch.float64)
+        dist.all_reduce(t)
+        return [tuple(t.tolist())]
+
+    tags = [f"k{k}" for k in KS] + (["full"] if fx.has(name, "full/iters") else [])
+    for tag in tags:
+        s.setMaxIterations(int(tag[1:]) if tag != "full" else -1)
+        x = s.solve(b)
+        parts = reduce_parts(check_against_reference(fx, name, tag, x, s.iterations(), s.error(), s.info(), row0=r0))
+        if not (bicg and tag in ("k50",)):
+            assert_close_to_reference(fx, name, tag, parts)
+        if rank == 0:
+            print(f"{name} x{world} {tag}: iterations {s.iterations()} error {s.error():.6e} "
+                  f"(reference {fx.get(name, tag + '/iters')}, {fx.get(name, tag + '/error'):.6e})", flush=True)
+    if "full" in tags:  # true residual with the distributed product
+        op = egm.SparseOperator(A, comm=comm)
+        r = b - op.multiply(x)
+        t = torch.tensor([float(r @ r), float(b @ b)], dtype=torch.float64)
+        dist.all_reduce(t)
+        res = float(np.sqrt(t[0] / t[1]))
+        assert res <= max(1.05 * TOL, 1.05 * fx.get(name, "full/true_residual")), res
+        op.close()
+    s.close()
+    print(f"rank {rank}: fullsize ok ({name})")
     dist.barrier()
     dist.destroy_process_group()
 

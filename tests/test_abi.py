@@ -18,7 +18,8 @@ def declared_symbols():
 def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for s in ("b200s_create", "b200s_destroy", "b200s_analyze_pattern", "b200s_factorize_f64", "b200s_spmv_f64",
-              "b200s_cg_solve_f64", "b200s_bicgstab_solve_f64", "b200s_get_stats", "b200s_last_error"):
+              "b200s_cg_solve_f64", "b200s_bicgstab_solve_f64", "b200s_cg_solve_f32", "b200s_bicgstab_solve_f32",
+              "b200s_cg_solve_device_f32", "b200s_get_stats", "b200s_last_error", "b200s_plan_probe_span"):
         assert s in syms
 
 
@@ -27,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     missing = [s for s in declared_symbols() if not hasattr(L, s)]
     assert not missing, missing
-    assert L.b200s_version() == 100
+    assert L.b200s_version() == 200
 
 
 def test_no_torch_types_in_signatures():

@@ -22,3 +22,23 @@ def test_row_partitioned_solvers(world, name, loop_mode, monkeypatch):
     res = launch(world, "gpu", name, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-5000:]
     assert res.stdout.count("gpu ok") == world
+
+
+@pytest.mark.parametrize("world,name", [(2, "cg_256"), (8, "cg_256"), (8, "bicg_256"), (8, "cg_512"), (4, "cg_256")])
+def test_baseline_configs_row_partitioned_vs_reference(world, name):
+    """configs[1], [2] (256^3, full convergence + trajectories) and configs[4] (512^3, trajectories k <= 50) on N
+    GPUs against the unmodified reference's outputs (tests/golden/fullsize_v1.npz)."""
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    res = launch(world, "fullsize", name, timeout=850)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-5000:]
+    assert res.stdout.count("fullsize ok") == world
+
+
+@pytest.mark.parametrize("world", [2])
+def test_a_rank_that_fails_before_launch_does_not_hang_the_others(world):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    res = launch(world, "deadpeer", "poisson3d", timeout=300)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-5000:]
+    assert res.stdout.count("deadpeer ok") == world

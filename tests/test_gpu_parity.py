@@ -160,3 +160,105 @@ def test_residual_history_matches_oracle_trajectory(golden, egm, port):
         _, _, err_k, _ = port.cg(A, b, tol=1e-300, max_iters=k)  # error() after k iterations = sqrt(rr_k/bb)
         # iteration k+1's first half produced rr that the oracle reports when stopping at max_iters = k
         assert abs(np.sqrt(hist[k - 1] / bb) - err_k) <= 1e-9 * err_k
+
+
+# ---------------------------------------------------------------------------------------------- round 2 additions
+@pytest.mark.parametrize("case", golden_case_names("bicgstab_restart"))
+@pytest.mark.parametrize("loop_mode", [1, 2, 3])
+def test_bicgstab_restart_branch(case, loop_mode, golden, egm):
+    """BiCGSTAB.h:72-81 live on the GPU: systems on which the reference restarts (once; one case twice).  The restart
+    count (from the bit-pinned port, see make_golden_v2.py), iterations() -- including "reset i only on the first
+    restart" -- and info() must be identical in every loop mode, x and error() equal to rounding."""
+    A = golden.matrix(case)
+    b = golden.get(case, "b")
+    s = egm.BiCGSTAB(A, preconditioner=int(golden.get(case, "precond")), loop_mode=loop_mode, chunk_iters=3)
+    s.setTolerance(float(golden.get(case, "tol")))
+    mi = int(golden.get(case, "max_iters"))
+    if mi >= 0:
+        s.setMaxIterations(mi)
+    x = s.solve(b)
+    xr = golden.get(case, "x_v4")
+    assert s.stats()["last_restarts"] == int(golden.get(case, "restarts")), (s.stats()["last_restarts"], case)
+    assert s.iterations() == int(golden.get(case, "iters_v4")) and s.info() == int(golden.get(case, "info_v4"))
+    assert np.linalg.norm(x - xr) <= 1e-9 * max(1.0, np.linalg.norm(xr)), np.linalg.norm(x - xr)
+    errr = float(golden.get(case, "error_v4"))
+    assert abs(s.error() - errr) <= 1e-6 * errr + 1e-11
+    s.close()
+
+
+def _check_f32(case, golden, x, it, err, info, tol):
+    xr = golden.get(case, "x_v4").astype(np.float64)
+    itr, infor = int(golden.get(case, "iters_v4")), int(golden.get(case, "info_v4"))
+    it3, info3 = int(golden.get(case, "iters_v3")), int(golden.get(case, "info_v3"))
+    name = case.split("/")[-1]
+    nx = np.linalg.norm(xr)
+    rel = np.linalg.norm(x.astype(np.float64) - xr) / nx if nx > 0 else np.linalg.norm(x)
+    if name == "zero_rhs":
+        assert not x.any() and it == itr and info == infor and err == float(golden.get(case, "error_v4"))
+        return
+    if name.startswith("traj_k"):
+        assert it == itr and info == infor
+        assert rel <= 2e-5, rel          # k steps of float arithmetic; dots are summed in a different order
+        return
+    # the reference's own precision for float is 1e-3 (test/main.h:409-415)
+    assert rel <= 1e-3, rel
+    if name == "default_tol":
+        return  # tolerance = FLT_EPSILON: both run into rounding noise (see the double counterpart)
+    if infor == info3:
+        assert info == infor, (info, infor)
+    spread = abs(itr - it3)
+    assert abs(it - itr) <= max(2, int(0.05 * itr), 3 * spread), (it, itr, it3)
+    if info == 0:
+        assert err <= tol
+
+
+@pytest.mark.parametrize("case", golden_case_names("cg_f32") + golden_case_names("bicgstab_f32"))
+def test_float_solver_golden(case, golden, egm):
+    """ConjugateGradient<SparseMatrix<float>> / BiCGSTAB<SparseMatrix<float>> (f1 of SURVEY 8f): vectors and scalar
+    recurrences in float, against the float instantiation of the unmodified reference."""
+    x, it, err, info, tol = _solve(egm, golden, case)
+    assert x.dtype == np.float32
+    _check_f32(case, golden, x, it, err, info, tol)
+
+
+@pytest.mark.parametrize("case", ["cg_f32/varcoef3d_10/pre1", "cg_f32/poisson2d_24/guess"])
+@pytest.mark.parametrize("loop_mode", [2, 3, 4])
+def test_float_loop_modes_agree(case, loop_mode, golden, egm):
+    base = _solve(egm, golden, case, loop_mode=1)
+    other = _solve(egm, golden, case, loop_mode=loop_mode, chunk_iters=5)
+    assert np.array_equal(base[0], other[0]) and base[1:4] == other[1:4]
+
+
+def test_loop_modes_agree_beyond_one_sweep(egm):
+    """Above n/2 = grid*256 elements the persistent kernel and the graph kernels group their partial sums differently
+    (documented in kernels.cuh): both must meet the parity bar against each other -- same iteration count, x equal to
+    1e-10 -- and each must be bitwise reproducible."""
+    from eigen_git_mirror_b200 import workloads as wl
+    A = wl.varcoef3d(80)  # 512,000 rows
+    b = np.asarray(A.to_scipy() @ wl.random_vector(A.rows, 12345))
+    out = {}
+    for mode in (1, 4):
+        s = egm.ConjugateGradient(A, loop_mode=mode)
+        s.setTolerance(1e-10)
+        x = s.solve(b)
+        x2 = s.solve(b)
+        assert np.array_equal(x, x2)
+        out[mode] = (x, s.iterations(), s.error(), s.info())
+        s.close()
+    assert out[1][3] == out[4][3] == 0 and abs(out[1][1] - out[4][1]) <= 1
+    assert np.linalg.norm(out[1][0] - out[4][0]) <= 1e-10 * np.linalg.norm(out[1][0])
+
+
+def test_nonfinite_residual_reports_what_the_reference_reports(egm):
+    """A NaN in b: the reference's CG iterates on NaNs until maxIterations and returns NoConvergence, iterations() ==
+    maxIterations(), error() = NaN, x = NaN.  The GPU loop stops at once and reports the same outputs."""
+    from eigen_git_mirror_b200 import workloads as wl
+    A = wl.poisson2d(16)
+    b = np.ones(A.rows)
+    b[7] = np.nan
+    s = egm.ConjugateGradient(A)
+    s.setMaxIterations(25)
+    x = s.solve(b)
+    assert s.info() == egm.NoConvergence and s.iterations() == 25 and np.isnan(s.error()) and np.isnan(x).all()
+    assert s.stats()["last_nonfinite"] != 0
+    s.close()

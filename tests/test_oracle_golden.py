@@ -100,3 +100,42 @@ def test_both_isa_variants_are_reproduced(forced, golden, port):
     A = golden.matrix(case)
     y = port.spmv(A, golden.get(case, "x"), blk=4 if forced == "v3" else 8)
     assert np.array_equal(y, golden.get(case, f"y_{forced}"))
+
+
+# ---------------------------------------------------------------------------------------------- round 2 additions
+@pytest.mark.parametrize("case", golden_case_names("bicgstab_restart"))
+def test_restart_branch_bit_exact_and_counted(case, golden, port):
+    """Systems on which the reference takes BiCGSTAB.h:72-81 (tests/golden/make_golden_v2.py): the port reproduces the
+    AVX-512 reference bit for bit at every maxIterations, so its restart count is the reference's."""
+    x, it, err, info = port.bicgstab(golden.matrix(case), golden.get(case, "b"), tol=float(golden.get(case, "tol")),
+                                     max_iters=int(golden.get(case, "max_iters")),
+                                     precond=int(golden.get(case, "precond")), lanes=8)
+    assert port.last_restarts == int(golden.get(case, "restarts"))
+    assert it == int(golden.get(case, "iters_v4")) and err == float(golden.get(case, "error_v4"))
+    assert np.array_equal(x, golden.get(case, "x_v4"))
+    # the AVX2 build of the reference takes the same branches
+    assert int(golden.get(case, "iters_v3")) == it
+
+
+def test_restart_goldens_do_restart(golden):
+    full = [c for c in golden_case_names("bicgstab_restart") if c.endswith("/full")]
+    counts = sorted(int(golden.get(c, "restarts")) for c in full)
+    assert len(full) == 7 and counts[0] >= 1 and counts[-1] == 2
+    # "reset i only on the first restart" (BiCGSTAB.h:80): the twice-restarting case reports more iterations than
+    # its second restart alone would leave
+    c = [c for c in full if int(golden.get(c, "restarts")) == 2][0]
+    assert int(golden.get(c, "iters_v4")) == 6
+
+
+@pytest.mark.parametrize("case", golden_case_names("cg_f32") + golden_case_names("bicgstab_f32"))
+def test_float_solver_port_tracks_reference(case, golden, port, variant):
+    """Float instantiations: the port follows the reference's control flow exactly (iterations, info) on the fixed-k
+    and trivial cases and to rounding elsewhere; bit-exactness of float solves is not claimed."""
+    x, it, err, info = _run(port, golden, case)
+    xr = golden.get(case, f"x_{variant}").astype(np.float64)
+    name = case.split("/")[-1]
+    if name.startswith("traj_k") or name == "zero_rhs":
+        assert it == int(golden.get(case, f"iters_{variant}")) and info == int(golden.get(case, f"info_{variant}"))
+    nx = np.linalg.norm(xr)
+    if nx > 0:
+        assert np.linalg.norm(x.astype(np.float64) - xr) / nx <= 1e-3

@@ -63,9 +63,9 @@ def test_invalid_inputs_are_rejected():
     bad.colidx[3] = A.cols + 5
     with pytest.raises(egm.B200Error):
         planning.probe(bad)
+    # rectangular matrices are fine for the product (the solvers reject them at solve time)
     rect = wl.CsrMatrix(3, 4, np.array([0, 1, 2, 3], np.int32), np.array([0, 1, 3], np.int32), np.ones(3))
-    with pytest.raises(egm.B200Error):
-        planning.probe(rect)
+    assert planning.probe(rect).stats["cols"] == 4
 
 
 def _dense_from(rowptr, colidx, vals, n):
@@ -120,3 +120,78 @@ def test_compressed_full_input_is_passed_through():
     A = wl.poisson2d(9)
     rp, ci, src = planning.canonical_csr(A)
     assert np.array_equal(rp, A.rowptr) and np.array_equal(ci, A.colidx) and np.array_equal(src, np.arange(A.nnz))
+
+
+def _span(A, uplo=3, inner_nnz=None):
+    from eigen_git_mirror_b200 import _lib
+    from eigen_git_mirror_b200.solvers import _ptr
+    inz = None if inner_nnz is None else np.ascontiguousarray(inner_nnz, np.int32)
+    return _lib.lib().b200s_plan_probe_span(A.rows, int(A.colidx.shape[0]), _ptr(A.rowptr), _ptr(A.colidx), _ptr(inz), uplo)
+
+
+@pytest.mark.parametrize("uplo", [3, 1])
+def test_rebased_rowptr_reads_the_right_slots(uplo):
+    """A Map / Ref of an inner panel: rowptr[0] = base > 0.  Entry k takes its value from slot base + k, and the
+    number of value slots factorize stages must reach past the last of them (round-1 advisor finding)."""
+    A = wl.poisson2d(6)
+    base = 5
+    rowptr = (A.rowptr + base).astype(np.int32)
+    colidx = np.concatenate([np.full(base, 0, np.int32), A.colidx])
+    vals = np.concatenate([np.full(base, np.nan), A.vals])
+    R = wl.CsrMatrix(A.rows, A.cols, rowptr, colidx, vals)
+    rp, ci, src = planning.canonical_csr(R, uplo=uplo)
+    assert src.min() >= base and src.max() < _span(R, uplo) == base + A.nnz
+    got = _dense_from(rp, ci, vals[src], A.rows)
+    assert np.array_equal(got, A.to_scipy().toarray())
+    # the binding may pass either the entry count or the slot count as nnz
+    R2 = wl.CsrMatrix(A.rows, A.cols, rowptr, colidx[: base + A.nnz], vals)
+    assert _span(R2, uplo) == base + A.nnz
+
+
+def test_span_of_uncompressed_and_plain_inputs():
+    A = wl.poisson2d(5)
+    assert _span(A) == A.nnz
+    lens = np.diff(A.rowptr)
+    rowptr = np.zeros(A.rows + 1, np.int32)
+    rowptr[1:] = np.cumsum(lens + 2)
+    colidx = np.zeros(rowptr[-1], np.int32)
+    for i in range(A.rows):
+        colidx[rowptr[i]:rowptr[i] + lens[i]] = A.colidx[A.rowptr[i]:A.rowptr[i + 1]]
+    U = wl.CsrMatrix(A.rows, A.cols, rowptr, colidx, np.zeros(rowptr[-1]))
+    assert _span(U, inner_nnz=lens) == rowptr[-2] + lens[-1]
+    bad = wl.CsrMatrix(A.rows, A.cols, A.rowptr, A.colidx[:-3], A.vals[:-3])
+    with pytest.raises(Exception):
+        planning.probe(bad)  # rowptr references slots past nnz
+
+
+def test_indices_are_narrowed_to_int32_before_crossing_the_abi():
+    """A CsrMatrix built with int64 indices (np.cumsum, scipy with 64-bit indices) must not be read as int32 garbage."""
+    A = wl.poisson2d(7)
+    A64 = wl.CsrMatrix(A.rows, A.cols, A.rowptr.astype(np.int64), A.colidx.astype(np.int64), A.vals)
+    v = planning.probe(A64)
+    assert v.stats["nnz"] == A.nnz and np.array_equal(v.local_colidx, A.colidx)
+    big = wl.CsrMatrix(2, 2 ** 33, np.array([0, 1, 2], np.int64), np.array([0, 2 ** 32 + 5], np.int64), np.ones(2))
+    with pytest.raises(ValueError):
+        planning.probe(big)
+
+
+def test_rectangular_matrices_are_accepted_for_the_product():
+    import scipy.sparse as sp
+    S = sp.random(30, 70, density=0.1, random_state=np.random.default_rng(3)).tocsr()
+    S.sort_indices()
+    v = planning.probe(S)
+    assert v.stats["rows"] == 30 and v.stats["cols"] == 70 and v.stats["nnz"] == S.nnz
+
+
+def test_partition_rows_balances_bytes_when_given_rowptr():
+    from eigen_git_mirror_b200 import partition_rows
+    A = wl.powerlaw(50000, 16, seed=9)
+    even = partition_rows(A.rows, 8)
+    bal = partition_rows(A.rows, 8, rowptr=A.rowptr)
+    assert bal[0] == 0 and bal[-1] == A.rows and np.all(np.diff(bal) > 0)
+    cost = lambda st: np.diff(12 * A.rowptr[st].astype(np.int64) + 104 * st)
+    assert cost(bal).max() <= 1.02 * cost(bal).mean()
+    assert cost(bal).max() <= cost(even).max()
+    n = 16
+    P = wl.poisson3d(n)
+    assert np.array_equal(partition_rows(P.rows, 4, align=n * n, rowptr=P.rowptr), partition_rows(P.rows, 4, align=n * n))
