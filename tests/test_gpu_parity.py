@@ -163,7 +163,14 @@ def test_residual_history_matches_oracle_trajectory(golden, egm, port):
 
 
 # ---------------------------------------------------------------------------------------------- round 2 additions
-@pytest.mark.parametrize("case", golden_case_names("bicgstab_restart"))
+# case3 restarts in the reference only because its packet-ordered sums happen to cancel exactly (Jacobi scaling by 1/3
+# makes the operands inexact); any other summation order -- the GPU's, or the reference built for another ISA on
+# other sizes -- leaves |rho| ~ 1e-17 > eps^2 |r0|^2 and legitimately does not restart.  The other systems cancel
+# exactly in every order.  It stays pinned in the CPU oracle test.
+_RESTART_CASES = [c for c in golden_case_names("bicgstab_restart") if "/case3/" not in c]
+
+
+@pytest.mark.parametrize("case", _RESTART_CASES)
 @pytest.mark.parametrize("loop_mode", [1, 2, 3])
 def test_bicgstab_restart_branch(case, loop_mode, golden, egm):
     """BiCGSTAB.h:72-81 live on the GPU: systems on which the reference restarts (once; one case twice).  The restart
@@ -181,8 +188,11 @@ def test_bicgstab_restart_branch(case, loop_mode, golden, egm):
     assert s.stats()["last_restarts"] == int(golden.get(case, "restarts")), (s.stats()["last_restarts"], case)
     assert s.iterations() == int(golden.get(case, "iters_v4")) and s.info() == int(golden.get(case, "info_v4"))
     assert np.linalg.norm(x - xr) <= 1e-9 * max(1.0, np.linalg.norm(xr)), np.linalg.norm(x - xr)
-    errr = float(golden.get(case, "error_v4"))
-    assert abs(s.error() - errr) <= 1e-6 * errr + 1e-11
+    errr, tol = float(golden.get(case, "error_v4")), float(golden.get(case, "tol"))
+    if errr <= tol:
+        assert s.error() <= tol  # converged: what is left of the residual is rounding noise on both sides
+    else:
+        assert abs(s.error() - errr) <= 1e-6 * errr
     s.close()
 
 
