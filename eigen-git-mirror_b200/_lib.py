@@ -31,7 +31,7 @@ class Stats(C.Structure):
         ("last_solve_ms", C.c_double), ("last_h2d_ms", C.c_double), ("last_d2h_ms", C.c_double),
         ("last_kernel_launches", C.c_int64), ("last_iterations", C.c_int64), ("last_spmv_count", C.c_int64),
         ("device_bytes", C.c_int64), ("last_restarts", C.c_int64), ("last_nonfinite", C.c_int32),
-        ("last_comm_error", C.c_int32),
+        ("last_comm_error", C.c_int32), ("l2_persist", C.c_int32), ("reserved1", C.c_int32),
     ]
 
     def as_dict(self):
@@ -75,6 +75,10 @@ def lib() -> C.CDLL:
         for name in ("b200s_cg_solve_", "b200s_bicgstab_solve_", "b200s_cg_solve_device_",
                      "b200s_bicgstab_solve_device_"):
             getattr(L, name + sfx).argtypes = solve_args
+    multi_args = [H, i64, vp, i64, vp, i64, C.c_int, dbl, i64, vp, vp, vp]
+    L.b200s_cg_solve_multi_f64.argtypes = multi_args
+    L.b200s_cg_solve_multi_device_f64.argtypes = multi_args
+    L.b200s_multi_rhs_batch.argtypes = [H]
     L.b200s_get_stats.argtypes = [H, C.POINTER(Stats)]
     L.b200s_get_invdiag_f64.argtypes = [H, vp]
     L.b200s_get_timeline.argtypes = [H, vp, C.c_int]

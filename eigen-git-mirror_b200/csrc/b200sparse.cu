@@ -18,6 +18,7 @@
 
 #include "../../include/b200sparse.h"
 #include "kernels.cuh"
+#include "kernels_multi.cuh"
 
 using namespace b200s;
 
@@ -28,6 +29,7 @@ thread_local std::string g_create_error;
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  bool owned = true;  // false: a slice of the handle's vector window
   template <typename T>
   T* as() const { return static_cast<T*>(p); }
 };
@@ -39,6 +41,7 @@ struct GraphSet {
   cudaGraphExec_t body_exec = nullptr;
   int init_kernels = 0, body_kernels = 0, tail_kernels = 0, body_unroll = 1;
   bool built = false;
+  const void* tag = nullptr;  // address the graph's kernels were built around (rebuilt when it moves)
 };
 
 }  // namespace
@@ -61,7 +64,8 @@ struct b200s_handle {
   DevBuf rowptr, colidx, vals, src, tiles, invdiag, send_rows;
   // vectors (doubles unless noted); ext = [owned | ghost]
   DevBuf window;  // peer-visible: 4 extended slots + mailboxes + flags
-  size_t slot_bytes = 0, box_off = 0, flag_off = 0, halo_flag_off = 0, window_bytes = 0;
+  size_t slot_bytes = 0, slots_off = 0, box_off = 0, flag_off = 0, halo_flag_off = 0, window_bytes = 0;
+  int l2_persist = 0;  // the front of the window (r, Ap, D^-1, x, p) is marked persisting in L2
   std::vector<void*> peer_window;  // [world], IPC-mapped (self: window.p)
   std::vector<int64_t> all_rows, all_ghosts;
   DevBuf b, r, q, r0, s, t, yout;
@@ -70,12 +74,16 @@ struct b200s_handle {
   Scalars* hS = nullptr;  // pinned mirror
   double comm_timeout_ms = 20000.0;  // bound of every device-side wait on a peer (B200S_COMM_TIMEOUT_MS)
   // launch geometry
-  int spmv_grid = 0, spmv_stages = 0, spmv_smem = 0, vec_grid = 0;
+  int spmv_grid = 0, spmv_stages = 0, spmv_stages_f32 = 0, spmv_smem = 0, vec_grid = 0;
   int spmv_grid_f32 = 0, spmv_smem_f32 = 0;  // float tiles are smaller: more CTAs fit per SM
   int evict_first = 0;
   int pdl = 0;           // programmatic dependent launch between the solver kernels (B200S_PDL=1)
   int body_unroll = 1;   // iterations per WHILE-body (amortises the loop-back, keeps PDL edges inside the body)
   GraphSet cg, bicg;
+  // multi-column CG (kernels_multi.cuh): interleaved [rows][K] vectors, one control block per column
+  GraphSet cg_multi[4];  // K = 2, 4, 8 -> index log2(K)
+  DevBuf mx, mr, mp, mq, mb, mS, mpartials, mstage;
+  Scalars* hSm = nullptr;  // pinned mirror of the K control blocks
   size_t device_bytes = 0;
   // stats of the last call
   double last_solve_ms = 0, last_h2d_ms = 0, last_d2h_ms = 0;
@@ -105,6 +113,7 @@ int dev_alloc(b200s_handle* h, DevBuf& buf, size_t bytes, bool zero = false) {
     if (zero) CK(cudaMemsetAsync(buf.p, 0, buf.bytes, h->stream));
     return 0;
   }
+  if (buf.p && !buf.owned) return fail(h, B200S_ERR_INVALID, "internal: window slice too small");
   if (buf.p) {
     cudaFree(buf.p);
     h->device_bytes -= buf.bytes;
@@ -123,12 +132,13 @@ int dev_alloc(b200s_handle* h, DevBuf& buf, size_t bytes, bool zero = false) {
 }
 
 void dev_free(b200s_handle* h, DevBuf& buf) {
-  if (buf.p) {
+  if (buf.p && buf.owned) {
     cudaFree(buf.p);
     h->device_bytes -= buf.bytes;
   }
   buf.p = nullptr;
   buf.bytes = 0;
+  buf.owned = true;
 }
 
 void destroy_graphs(GraphSet& g) {
@@ -145,14 +155,22 @@ int env_int(const char* name, int dflt) {
 }
 
 // ---- window layout (identical arithmetic on every rank, for every rank) ----
+// ONE allocation per handle holds every vector of the solvers:
+//   [ r | q | invdiag | slot X | slot P | slot Z | slot Spmv | mailboxes | flags | halo flags | b | r0 | s | t | yout ]
+// The four slots are extended vectors [owned | ghost] that peers store into (the allocation is exported over CUDA
+// IPC); the others are private.  The order puts the five vectors a CG iteration touches (r, Ap, D^-1, x, p) at the
+// front, contiguous, so that ONE L2 access-policy window can mark exactly them as persisting (see l2_persist).
 size_t ext_slot_bytes(int64_t rows, int64_t ghosts) {
   return ((static_cast<size_t>(rows + ghosts) * 8 + 255) & ~size_t(255)) + 256;
 }
+size_t priv_vec_bytes(int64_t rows) { return ((static_cast<size_t>(rows) * 8 + 255) & ~size_t(255)) + 256; }
 enum { kSlotX = 0, kSlotP = 1, kSlotZ = 2, kSlotSpmv = 3, kNumSlots = 4 };
+enum { kFrontVecs = 3 /* r, q, invdiag */, kBackVecs = 5 /* b, r0, s, t, yout */ };
+size_t slots_off(int64_t rows) { return kFrontVecs * priv_vec_bytes(rows); }
 
 template <typename T>
 T* slot_ptr(const b200s_handle* h, int slot) {
-  return reinterpret_cast<T*>(static_cast<char*>(h->window.p) + h->slot_bytes * slot);
+  return reinterpret_cast<T*>(static_cast<char*>(h->window.p) + h->slots_off + h->slot_bytes * slot);
 }
 
 CommDev make_comm(const b200s_handle* h) {
@@ -167,7 +185,7 @@ CommDev make_comm(const b200s_handle* h) {
     // offsets inside a peer's window depend on that peer's slot size
     size_t sb = ext_slot_bytes(h->all_rows[q], h->all_ghosts[q]);
     char* base = static_cast<char*>(h->peer_window[q]);
-    size_t box_off = sb * kNumSlots;
+    size_t box_off = slots_off(h->all_rows[q]) + sb * kNumSlots;
     size_t flag_off = box_off + sizeof(unsigned long long) * 2 * kMaxWorld * kBoxWords;
     size_t halo_off = flag_off + sizeof(unsigned) * 2 * kMaxWorld;
     c.box_peer[q] = reinterpret_cast<double*>(base + box_off);
@@ -246,7 +264,7 @@ int make_spmv_args(b200s_handle* h, SpmvArgs<T>& a, const T* x_ext, T* y, const 
   a.x = x_ext;
   a.y = y;
   a.w = w;
-  a.stages = h->spmv_stages;
+  a.stages = sizeof(T) == 4 ? h->spmv_stages_f32 : h->spmv_stages;
   a.cap_nnz = h->plan.tile_nnz;
   a.cap_rows = h->plan.tile_rows_cap;
   a.tail_blk = (sizeof(T) == 4) ? 8 : 0;
@@ -269,7 +287,7 @@ int make_spmv_args(b200s_handle* h, SpmvArgs<T>& a, const T* x_ext, T* y, const 
       a.halo.send_offsets[q] = h->plan.send_offsets[q];
       a.halo.send_counts[q] = h->plan.send_counts[q];
       size_t sb = ext_slot_bytes(h->all_rows[q], h->all_ghosts[q]);
-      char* base = static_cast<char*>(h->peer_window[q]) + sb * halo_slot;
+      char* base = static_cast<char*>(h->peer_window[q]) + slots_off(h->all_rows[q]) + sb * halo_slot;
       a.halo.dst[q] = reinterpret_cast<T*>(base) + h->all_rows[q] + h->plan.send_slot0[q];
     }
   }
@@ -508,19 +526,119 @@ int build_graphs(b200s_handle* h, GraphSet& g, enqueue_fn init, enqueue_fn body,
   return 0;
 }
 
-int ensure_solver_buffers(b200s_handle* h, bool bicg) {
-  const size_t vb = static_cast<size_t>(h->plan.rows) * 8;
-  int rc;
-  if ((rc = dev_alloc(h, h->b, vb))) return rc;
-  if ((rc = dev_alloc(h, h->r, vb))) return rc;
-  if ((rc = dev_alloc(h, h->q, vb))) return rc;
-  if (bicg) {
-    if ((rc = dev_alloc(h, h->r0, vb))) return rc;
-    if ((rc = dev_alloc(h, h->s, vb))) return rc;
-    if ((rc = dev_alloc(h, h->t, vb))) return rc;
-    if ((rc = dev_alloc(h, h->yout, vb))) return rc;
-  }
+// ---- multi-column CG ------------------------------------------------------------------------------------------
+// The K-wide kernels cover row-lane tiles only; matrices with two-phase or long-row tiles (strongly irregular rows),
+// float factorizations and row-partitioned handles take the sequential per-column path, like the reference does.
+bool multi_supported(const b200s_handle* h) {
+  return h->factorized && h->scalar_bytes == 8 && h->plan.world == 1 && h->plan.n_stream == 0 && h->plan.n_long == 0 &&
+         h->spmv_impl != B200S_SPMV_DIRECT && h->plan.rows == h->plan.cols && h->plan.rows > 0;
+}
+
+template <int K>
+MultiArgs<K> make_multi(b200s_handle* h, int epilogue, int gate, bool set_cond, cudaGraphConditionalHandle cond) {
+  MultiArgs<K> a{};
+  a.n = h->plan.rows;
+  a.x = h->mx.as<double>();
+  a.r = h->mr.as<double>();
+  a.p = h->mp.as<double>();
+  a.q = h->mq.as<double>();
+  a.b = h->mb.as<double>();
+  a.invdiag = h->invdiag.as<double>();
+  a.S = h->mS.as<Scalars>();
+  a.partials = h->mpartials.as<double>();
+  a.counter = h->counter.as<unsigned>();
+  a.cond_handle = static_cast<unsigned long long>(cond);
+  a.set_cond = set_cond ? 1 : 0;
+  a.epilogue = epilogue;
+  a.gate = gate;
+  return a;
+}
+
+template <int K>
+int launch_spmm(b200s_handle* h, const double* x, double* y, int ndot, int epilogue, int gate) {
+  SpmmArgs<K> a{};
+  int rc = make_spmv_args<double>(h, a.sp, nullptr, nullptr, nullptr, kEpiNone, kGateNone, false, 0, -1);
+  if (rc) return rc;
+  a.m = make_multi<K>(h, epilogue, gate, false, 0);
+  a.x = x;
+  a.y = y;
+  a.ndot = ndot;
+  CK(cudaFuncSetAttribute((const void*)spmm_staged_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->spmv_smem));
+  // the SAME grid as the single-column product: the grouping of the per-CTA partial sums is part of the result
+  launch_k(h, spmm_staged_kernel<K>, h->spmv_grid, kSpmvThreads, static_cast<size_t>(h->spmv_smem), a);
+  CK(cudaGetLastError());
+  h->last_launches++;
   return 0;
+}
+
+template <int K>
+int enqueue_cg_multi_init(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
+  int rc;
+  if ((rc = launch_spmm<K>(h, h->mx.as<double>(), h->mq.as<double>(), 0, kEpiNone, kGateGuess))) return rc;
+  MultiArgs<K> a = make_multi<K>(h, kEpiCgInit, kGateNone, set_cond, cond);
+  LAUNCH_VEC(cg_init_multi_kernel<K>, a);
+  return 0;
+}
+
+template <int K>
+int enqueue_cg_multi_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle cond) {
+  int rc;
+  if ((rc = launch_spmm<K>(h, h->mp.as<double>(), h->mq.as<double>(), 1, kEpiCgPAp, kGateLoop))) return rc;
+  MultiArgs<K> u = make_multi<K>(h, kEpiCgUpdate, kGateLoop, set_cond, cond);
+  LAUNCH_VEC(cg_update_multi_kernel<K>, u);
+  MultiArgs<K> d = make_multi<K>(h, kEpiNone, kGateNone, false, 0);
+  CK(launch_k(h, cg_direction_multi_kernel<K>, h->vec_grid, kVecThreads, 0, d, h->gridbar.as<unsigned>() + 64));
+  h->last_launches++;
+  return 0;
+}
+
+template <int K>
+int enqueue_multi_finalize(b200s_handle* h) {
+  MultiArgs<K> a = make_multi<K>(h, kEpiNone, kGateNone, false, 0);
+  LAUNCH_VEC(finalize_multi_kernel<K>, a);
+  return 0;
+}
+
+int ensure_solver_buffers(b200s_handle* h, bool) {
+  // every solver vector is a slice of the window allocation made by analyze_pattern
+  if (!h->b.p || !h->r.p || !h->q.p || !h->r0.p || !h->s.p || !h->t.p || !h->yout.p)
+    return fail(h, B200S_ERR_INVALID, "solve: call analyze_pattern first");
+  return 0;
+}
+
+// Runs init -> loop -> finalize in the handle's loop mode.  `stop_flag` points into the pinned mirror `host` of the
+// device control block(s) `dev`; the host-driven modes poll it between launches.
+int drive_loop(b200s_handle* h, GraphSet& g, enqueue_fn init, enqueue_fn body, int (*finalize)(b200s_handle*),
+               int (*persistent)(b200s_handle*), bool while_graph, const int* stop_flag, void* host, void* dev,
+               size_t bytes) {
+  int rc;
+  if (persistent) {
+    if ((rc = init(h, false, 0))) return rc;
+    if ((rc = persistent(h))) return rc;
+    return finalize(h);
+  }
+  if (while_graph) {
+    CK(cudaGraphLaunch(g.exec, h->stream));
+    return 0;
+  }
+  if (h->loop_mode == B200S_LOOP_CHUNKED_GRAPH) {
+    CK(cudaGraphLaunch(g.exec, h->stream));
+    h->last_launches += g.init_kernels;
+  } else {
+    if ((rc = init(h, false, 0))) return rc;
+  }
+  for (;;) {
+    CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (*stop_flag) break;
+    if (h->loop_mode == B200S_LOOP_CHUNKED_GRAPH) {
+      CK(cudaGraphLaunch(g.body_exec, h->stream));
+      h->last_launches += g.body_kernels;
+    } else {
+      if ((rc = body(h, false, 0))) return rc;
+    }
+  }
+  return finalize(h);
 }
 
 // Row-partitioned runs: all ranks agree that everybody got this far before anything that waits on a peer is
@@ -579,32 +697,10 @@ int run_solve(b200s_handle* h, bool bicg, const T* b_dev, T* x_dev, int use_gues
   CK(cudaEventRecord(h->ev0, h->stream));
   const bool persistent = (h->loop_mode == B200S_LOOP_PERSISTENT) && !bicg && h->spmv_impl != B200S_SPMV_DIRECT;
   const bool while_graph = (h->loop_mode == B200S_LOOP_WHILE_GRAPH) || (h->loop_mode == B200S_LOOP_PERSISTENT && !persistent);
-  if (persistent) {
-    if ((rc = enqueue_cg_init<T>(h, false, 0))) return rc;
-    if ((rc = launch_cg_persistent<T>(h))) return rc;
-    if ((rc = enqueue_finalize<T>(h))) return rc;
-  } else if (while_graph) {
-    CK(cudaGraphLaunch(g.exec, h->stream));
-  } else {
-    if (h->loop_mode == B200S_LOOP_CHUNKED_GRAPH) {
-      CK(cudaGraphLaunch(g.exec, h->stream));
-      h->last_launches += g.init_kernels;
-    } else {
-      if ((rc = (bicg ? enqueue_bicg_init<T> : enqueue_cg_init<T>)(h, false, 0))) return rc;
-    }
-    for (;;) {
-      CK(cudaMemcpyAsync(h->hS, h->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      if (h->hS->stop) break;
-      if (h->loop_mode == B200S_LOOP_CHUNKED_GRAPH) {
-        CK(cudaGraphLaunch(g.body_exec, h->stream));
-        h->last_launches += g.body_kernels;
-      } else {
-        if ((rc = (bicg ? enqueue_bicg_body<T> : enqueue_cg_body<T>)(h, false, 0))) return rc;
-      }
-    }
-    if ((rc = enqueue_finalize<T>(h))) return rc;
-  }
+  if ((rc = drive_loop(h, g, bicg ? enqueue_bicg_init<T> : enqueue_cg_init<T>, bicg ? enqueue_bicg_body<T> : enqueue_cg_body<T>,
+                       enqueue_finalize<T>, persistent ? launch_cg_persistent<T> : nullptr, while_graph, &h->hS->stop,
+                       h->hS, h->scalars.p, sizeof(Scalars))))
+    return rc;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaMemcpyAsync(h->hS, h->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
   if (x_dev != x_int) CK(cudaMemcpyAsync(x_dev, x_int, n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
@@ -662,6 +758,120 @@ int run_solve(b200s_handle* h, bool bicg, const T* b_dev, T* x_dev, int use_gues
   return 0;
 }
 
+// One batch of K (2, 4 or 8) columns, device-resident column-major B / X (leading dimensions ldb / ldx >= rows).
+template <int K>
+int run_solve_multi(b200s_handle* h, int ncols, const double* B_dev, int64_t ldb, double* X_dev, int64_t ldx,
+                    int use_guess, double tol, int64_t max_iters, int64_t* iters_out, double* error_out,
+                    int* info_out) {
+  constexpr int LOGK = (K == 2) ? 1 : (K == 4) ? 2 : 3;
+  const int64_t n = h->plan.rows;
+  const size_t vb = static_cast<size_t>(n) * K * 8;
+  int rc;
+  if ((rc = dev_alloc(h, h->mx, vb))) return rc;
+  if ((rc = dev_alloc(h, h->mr, vb))) return rc;
+  if ((rc = dev_alloc(h, h->mp, vb))) return rc;
+  if ((rc = dev_alloc(h, h->mq, vb))) return rc;
+  if ((rc = dev_alloc(h, h->mb, vb))) return rc;
+  if ((rc = dev_alloc(h, h->mS, sizeof(Scalars) * kMultiMax, false))) return rc;
+  if ((rc = dev_alloc(h, h->mpartials, sizeof(double) * kMaxGrid * kMultiPartialStride, false))) return rc;
+  if (!h->hSm) CK(cudaMallocHost(reinterpret_cast<void**>(&h->hSm), sizeof(Scalars) * kMultiMax));
+  GraphSet& g = h->cg_multi[LOGK];
+  if (g.built && (g.tag != h->mx.p)) destroy_graphs(g);  // the vectors were reallocated: graphs bake pointers
+  if ((rc = build_graphs(h, g, enqueue_cg_multi_init<K>, enqueue_cg_multi_body<K>, enqueue_multi_finalize<K>))) return rc;
+  g.tag = h->mx.p;
+
+  if (tol < 0) tol = std::numeric_limits<double>::epsilon();
+  if (max_iters < 0) max_iters = 2 * h->plan.cols;
+  const int ig = std::max(1, std::min(h->sm_count * 8, static_cast<int>((n + 255) / 256)));
+  interleave_kernel<K><<<ig, 256, 0, h->stream>>>(n, ncols, B_dev, ldb, h->mb.as<double>());
+  if (use_guess) interleave_kernel<K><<<ig, 256, 0, h->stream>>>(n, ncols, X_dev, ldx, h->mx.as<double>());
+  CK(cudaGetLastError());
+  std::memset(h->hSm, 0, sizeof(Scalars) * kMultiMax);
+  for (int j = 0; j < K; ++j) {
+    h->hSm[j].tol = tol;
+    h->hSm[j].max_iters = max_iters;
+    h->hSm[j].use_guess = use_guess ? 1 : 0;
+  }
+  CK(cudaMemcpyAsync(h->mS.p, h->hSm, sizeof(Scalars) * kMultiMax, cudaMemcpyHostToDevice, h->stream));
+
+  h->last_launches = 0;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  const bool while_graph = (h->loop_mode == B200S_LOOP_WHILE_GRAPH) || (h->loop_mode == B200S_LOOP_PERSISTENT);
+  if ((rc = drive_loop(h, g, enqueue_cg_multi_init<K>, enqueue_cg_multi_body<K>, enqueue_multi_finalize<K>, nullptr,
+                       while_graph, &h->hSm[0].stop_all, h->hSm, h->mS.p, sizeof(Scalars) * kMultiMax)))
+    return rc;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  deinterleave_kernel<K><<<ig, 256, 0, h->stream>>>(n, ncols, h->mx.as<double>(), X_dev, ldx);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->hSm, h->mS.p, sizeof(Scalars) * kMultiMax, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_solve_ms += ms;
+  int64_t max_spmv = 0;
+  for (int j = 0; j < ncols; ++j) {
+    const Scalars& S = h->hSm[j];
+    int64_t iters;
+    double err;
+    if (S.rhs_zero) { iters = 0; err = 0.0; }                       // ConjugateGradient.h:46-52
+    else if (S.numerical_issue) { iters = max_iters; err = std::numeric_limits<double>::quiet_NaN(); }
+    else { iters = S.iter; err = std::sqrt(S.rr / S.bb); }          // :89
+    if (iters_out) iters_out[j] = iters;
+    if (error_out) error_out[j] = err;
+    if (info_out) info_out[j] = (err <= tol) ? 0 : 2;               // :220
+    max_spmv = std::max<int64_t>(max_spmv, S.spmv_count);
+    h->last_iterations = iters;
+    if (S.numerical_issue) h->last_nonfinite = S.numerical_issue;
+  }
+  h->last_spmv += max_spmv;
+  if (while_graph) {
+    const int64_t passes = std::max<int64_t>(0, max_spmv - (use_guess ? 1 : 0));
+    const int64_t wpasses = (passes + g.body_unroll - 1) / g.body_unroll;
+    h->last_launches = g.init_kernels + wpasses * g.body_unroll * g.body_kernels + g.tail_kernels;
+  }
+  return 0;
+}
+
+// Any number of columns: batches of 8 / 4 / 2 through the K-wide kernels, a last single column (or everything, when
+// the handle does not support batching) through the single-column solver.  Column-major, device pointers.
+int solve_multi_device(b200s_handle* h, int64_t ncols, const double* B, int64_t ldb, double* X, int64_t ldx,
+                       int use_guess, double tol, int64_t max_iters, int64_t* iters_out, double* error_out,
+                       int* info_out, int64_t* launches_out) {
+  const bool batched = multi_supported(h) && env_int("B200S_MULTI_RHS", 1) != 0;
+  double total_ms = 0;
+  int64_t launches = 0;
+  h->last_spmv = 0;
+  h->last_nonfinite = 0;
+  int64_t c = 0;
+  while (c < ncols) {
+    const int64_t left = ncols - c;
+    int64_t *it = iters_out ? iters_out + c : nullptr;
+    double* er = error_out ? error_out + c : nullptr;
+    int* in = info_out ? info_out + c : nullptr;
+    int rc, took;
+    h->last_solve_ms = 0;
+    if (batched && left >= 2) {
+      const int kmax = std::max(2, std::min(kMultiMax, env_int("B200S_MULTI_K", kMultiMax)));
+      if (left >= 5 && kmax >= 8) { took = static_cast<int>(std::min<int64_t>(8, left)); rc = run_solve_multi<8>(h, took, B + c * ldb, ldb, X + c * ldx, ldx, use_guess, tol, max_iters, it, er, in); }
+      else if (left >= 3 && kmax >= 4) { took = static_cast<int>(std::min<int64_t>(4, left)); rc = run_solve_multi<4>(h, took, B + c * ldb, ldb, X + c * ldx, ldx, use_guess, tol, max_iters, it, er, in); }
+      else { took = 2; rc = run_solve_multi<2>(h, took, B + c * ldb, ldb, X + c * ldx, ldx, use_guess, tol, max_iters, it, er, in); }
+    } else {
+      took = 1;
+      const int64_t spmv_before = h->last_spmv;
+      rc = run_solve<double>(h, false, B + c * ldb, X + c * ldx, use_guess, tol, max_iters, it, er, in);
+      h->last_spmv += spmv_before;
+    }
+    if (rc) return rc;
+    total_ms += h->last_solve_ms;
+    launches += h->last_launches;
+    c += took;
+  }
+  h->last_solve_ms = total_ms;
+  h->last_launches = launches;
+  if (launches_out) *launches_out = launches;
+  return 0;
+}
+
 template <typename T>
 int factorize_impl(b200s_handle* h, const T* values, int precond) {
   if (!h->analyzed) return fail(h, B200S_ERR_INVALID, "factorize: call analyze_pattern first (IterativeSolverBase.h:218 asserts m_analysisIsOk)");
@@ -675,6 +885,7 @@ int factorize_impl(b200s_handle* h, const T* values, int precond) {
   if (h->scalar_bytes != static_cast<int>(sizeof(T))) {  // graphs bake pointers/types: rebuild lazily
     destroy_graphs(h->cg);
     destroy_graphs(h->bicg);
+    for (GraphSet& g : h->cg_multi) destroy_graphs(g);
   }
   h->scalar_bytes = sizeof(T);
   h->precond = precond;
@@ -693,7 +904,6 @@ int factorize_impl(b200s_handle* h, const T* values, int precond) {
     CK(cudaStreamSynchronize(h->stream));
     dev_free(h, staging);
   }
-  if ((rc = dev_alloc(h, h->invdiag, static_cast<size_t>(p.rows) * sizeof(T)))) return rc;
   if (p.rows) {
     // the diagonal of local row j sits at local column j (owned columns are numbered like the rows)
     jacobi_factorize_kernel<T><<<static_cast<int>((p.rows + 255) / 256), 256, 0, h->stream>>>(
@@ -756,7 +966,6 @@ int spmv_host_impl(b200s_handle* h, const T* x, T* y) {
   const int64_t nx = (p.world == 1) ? p.cols : p.rows;
   T* xs = slot_ptr<T>(h, kSlotSpmv);
   int rc;
-  if ((rc = dev_alloc(h, h->yout, static_cast<size_t>(p.rows) * 8))) return rc;
   CK(cudaEventRecord(h->ev0, h->stream));
   CK(cudaMemcpyAsync(xs, x, static_cast<size_t>(nx) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -819,6 +1028,8 @@ int solve_device(b200s_handle* h, bool bicg, const T* b, T* x, int use_guess, do
   return run_solve<T>(h, bicg, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
 }
 
+int configure_l2_persistence(b200s_handle* h);
+
 int configure_spmv(b200s_handle* h) {
   // stage geometry is decided for the widest scalar (double) so that one plan serves both precisions
   const Plan& p = h->plan;
@@ -833,7 +1044,13 @@ int configure_spmv(b200s_handle* h) {
   if (stage * stages > 220 * 1024) return fail(h, B200S_ERR_INVALID, "tile_nnz/tile_rows too large for shared memory");
   h->spmv_stages = stages;
   h->spmv_smem = static_cast<int>(stage * stages);
-  h->spmv_smem_f32 = static_cast<int>(spmv_stage_bytes<float>(p.tile_nnz, p.tile_rows_cap) * stages);
+  // float tiles hold two thirds of the bytes of double tiles: one more stage gives the same bytes in flight per CTA
+  // in the same shared memory (a float tile drains in 2/3 of the time, so two stages do not cover the refill latency)
+  const size_t stage32 = spmv_stage_bytes<float>(p.tile_nnz, p.tile_rows_cap);
+  int stages32 = std::max(2, std::min(8, env_int("B200S_SPMV_STAGES_F32", stages + 1)));
+  while (stages32 > 2 && stage32 * stages32 > std::max(budget, stage * stages)) --stages32;
+  h->spmv_stages_f32 = stages32;
+  h->spmv_smem_f32 = static_cast<int>(stage32 * stages32);
   const void* fns[] = {(const void*)spmv_staged_kernel<double, 0>, (const void*)spmv_staged_kernel<double, 1>,
                        (const void*)spmv_staged_kernel<double, 2>};
   const void* fns32[] = {(const void*)spmv_staged_kernel<float, 0>, (const void*)spmv_staged_kernel<float, 1>,
@@ -894,6 +1111,45 @@ int configure_spmv(b200s_handle* h) {
   int lg = 0;
   while ((1 << lg) < std::max(1, mean / 2) && lg < 5) ++lg;
   h->direct_lg = lg;
+  return 0;
+}
+
+// L2 residency of the CG working set.  When the five vectors of a CG iteration (r, Ap, D^-1, x, p: the front of the
+// window) fit the persisting share of L2 while the matrix does not fit L2, they are marked persisting with a stream
+// access-policy window (captured into the graph's kernel nodes as well); the matrix stream already carries an
+// evict-first hint, so one iteration re-reads only the matrix from HBM.  This is the regime of strong scaling over
+// 8 GPUs (256^3 / 8 = 2.1 M rows per GPU: 84 MB of vectors, 176 MB of matrix, 126 MB of L2).
+int configure_l2_persistence(b200s_handle* h) {
+  h->l2_persist = 0;
+  cudaStreamAttrValue attr;
+  std::memset(&attr, 0, sizeof(attr));
+  const int want = env_int("B200S_L2_PERSIST", -1);  // -1 auto, 0 off, 1 force
+  int l2 = 0, max_persist = 0, max_window = 0;
+  CK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
+  CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device));
+  CK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device));
+  const Plan& p = h->plan;
+  const size_t hot = h->slots_off + 2 * h->slot_bytes;  // r, q, invdiag, slot X, slot P
+  const double mat_bytes = 12.0 * static_cast<double>(p.nnz) + 4.0 * static_cast<double>(p.rows);
+  bool on = want > 0;
+  if (want < 0)
+    on = max_persist > 0 && hot <= static_cast<size_t>(max_persist) && hot <= static_cast<size_t>(max_window) &&
+         mat_bytes + static_cast<double>(hot) > 1.0 * l2;
+  if (on && max_persist > 0 && max_window > 0) {
+    const size_t bytes = std::min(hot, static_cast<size_t>(max_window));
+    const size_t setaside = std::min(static_cast<size_t>(max_persist),
+                                     static_cast<size_t>(env_int("B200S_L2_PERSIST_MB", 0)) > 0
+                                         ? static_cast<size_t>(env_int("B200S_L2_PERSIST_MB", 0)) << 20
+                                         : bytes);
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside));
+    attr.accessPolicyWindow.base_ptr = h->window.p;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = static_cast<float>(std::min(1.0, static_cast<double>(setaside) / static_cast<double>(bytes)));
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    h->l2_persist = 1;
+  }
+  CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
   return 0;
 }
 
@@ -988,10 +1244,14 @@ void b200s_destroy(b200s_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   destroy_graphs(h->cg);
   destroy_graphs(h->bicg);
+  for (GraphSet& g : h->cg_multi) destroy_graphs(g);
+  if (h->hSm) cudaFreeHost(h->hSm);
   for (int q = 0; q < static_cast<int>(h->peer_window.size()); ++q)
     if (q != h->plan.rank && h->peer_window[q]) cudaIpcCloseMemHandle(h->peer_window[q]);
-  DevBuf* bufs[] = {&h->rowptr, &h->colidx, &h->vals, &h->src, &h->tiles, &h->invdiag, &h->send_rows, &h->window,
-                    &h->b, &h->r, &h->q, &h->r0, &h->s, &h->t, &h->yout, &h->scalars, &h->partials, &h->counter,
+  DevBuf* bufs[] = {&h->mx, &h->mr, &h->mp, &h->mq, &h->mb, &h->mS, &h->mpartials, &h->mstage,
+                    &h->b, &h->r, &h->q, &h->r0, &h->s, &h->t, &h->yout, &h->invdiag,  // slices first
+                    &h->rowptr, &h->colidx, &h->vals, &h->src, &h->tiles, &h->send_rows, &h->window,
+                    &h->scalars, &h->partials, &h->counter,
                     &h->halo_counter, &h->history, &h->gridbar};
   for (DevBuf* b : bufs) dev_free(h, *b);
   if (h->hS) cudaFreeHost(h->hS);
@@ -1008,6 +1268,7 @@ int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t n
   h->analyzed = h->factorized = false;
   destroy_graphs(h->cg);
   destroy_graphs(h->bicg);
+  for (GraphSet& g : h->cg_multi) destroy_graphs(g);
   std::string err;
   int rc = build_plan(h->cfg, rows, cols, nnz, rowptr, colidx, inner_nnz, uplo, row_starts, h->plan, err);
   if (rc) return fail(h, rc, err);
@@ -1051,15 +1312,29 @@ int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t n
     h->all_ghosts[0] = mine[1];
   }
   h->slot_bytes = ext_slot_bytes(mine[0], mine[1]);
-  h->box_off = h->slot_bytes * kNumSlots;
+  h->slots_off = slots_off(mine[0]);
+  h->box_off = h->slots_off + h->slot_bytes * kNumSlots;
   h->flag_off = h->box_off + sizeof(unsigned long long) * 2 * kMaxWorld * kBoxWords;
   h->halo_flag_off = h->flag_off + sizeof(unsigned) * 2 * kMaxWorld;
-  h->window_bytes = h->halo_flag_off + sizeof(unsigned) * kMaxWorld + 256;
+  const size_t back_off = (h->halo_flag_off + sizeof(unsigned) * kMaxWorld + 511) & ~size_t(255);
+  const size_t pv = priv_vec_bytes(mine[0]);
+  h->window_bytes = back_off + kBackVecs * pv;
   for (int q = 0; q < static_cast<int>(h->peer_window.size()); ++q)
     if (q != p.rank && h->peer_window[q]) cudaIpcCloseMemHandle(h->peer_window[q]);
   h->peer_window.assign(W, nullptr);
-  if (h->window.p) { dev_free(h, h->window); }
-  if ((rc = dev_alloc(h, h->window, h->window_bytes, true))) return rc;
+  {
+    DevBuf* slices[] = {&h->r, &h->q, &h->invdiag, &h->b, &h->r0, &h->s, &h->t, &h->yout};
+    for (DevBuf* sl : slices) dev_free(h, *sl);
+    if (h->window.p) { dev_free(h, h->window); }
+    if ((rc = dev_alloc(h, h->window, h->window_bytes, true))) return rc;
+    char* base = static_cast<char*>(h->window.p);
+    for (int i = 0; i < 8; ++i) {
+      slices[i]->p = base + (i < kFrontVecs ? i * pv : back_off + (i - kFrontVecs) * pv);
+      slices[i]->bytes = pv;
+      slices[i]->owned = false;
+    }
+  }
+  if ((rc = configure_l2_persistence(h))) return rc;
   CK(cudaStreamSynchronize(h->stream));
   h->peer_window[p.rank] = h->window.p;
   if (W > 1) {
@@ -1111,6 +1386,59 @@ B200S_SOLVE_ENTRY(b200s_cg_solve_device_f32, float, solve_device, false)
 B200S_SOLVE_ENTRY(b200s_bicgstab_solve_device_f32, float, solve_device, true)
 #undef B200S_SOLVE_ENTRY
 
+int b200s_multi_rhs_batch(b200s_handle* h) { return (h && multi_supported(h)) ? kMultiMax : 0; }
+
+int b200s_cg_solve_multi_device_f64(b200s_handle* h, int64_t ncols, const double* B_dev, int64_t ldb, double* X_dev,
+                                    int64_t ldx, int use_guess, double tol, int64_t max_iters, int64_t* iters_out,
+                                    double* error_out, int* info_out) {
+  if (!h) return B200S_ERR_INVALID;
+  if (!h->factorized) return fail(h, B200S_ERR_INVALID, "solve: call analyze_pattern + factorize first");
+  if (h->scalar_bytes != 8) return fail(h, B200S_ERR_INVALID, "solve_multi: the matrix was factorized in float");
+  if (ncols < 0 || (ncols > 0 && (!B_dev || !X_dev)) || ldb < h->plan.rows || ldx < h->plan.rows)
+    return fail(h, B200S_ERR_INVALID, "solve_multi: bad argument");
+  CK(cudaSetDevice(h->device));
+  return solve_multi_device(h, ncols, B_dev, ldb, X_dev, ldx, use_guess, tol, max_iters, iters_out, error_out, info_out,
+                            nullptr);
+}
+
+int b200s_cg_solve_multi_f64(b200s_handle* h, int64_t ncols, const double* B, int64_t ldb, double* X, int64_t ldx,
+                             int use_guess, double tol, int64_t max_iters, int64_t* iters_out, double* error_out,
+                             int* info_out) {
+  if (!h) return B200S_ERR_INVALID;
+  if (!h->factorized) return fail(h, B200S_ERR_INVALID, "solve: call analyze_pattern + factorize first");
+  if (h->scalar_bytes != 8) return fail(h, B200S_ERR_INVALID, "solve_multi: the matrix was factorized in float");
+  const int64_t n = h->plan.rows;
+  if (ncols < 0 || (ncols > 0 && (!B || !X)) || ldb < n || ldx < n) return fail(h, B200S_ERR_INVALID, "solve_multi: bad argument");
+  if (ncols == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  int rc;
+  // device staging: [B | X], column-major with leading dimension n
+  if ((rc = dev_alloc(h, h->mstage, static_cast<size_t>(n) * ncols * 16))) return rc;
+  double* Bd = h->mstage.as<double>();
+  double* Xd = Bd + static_cast<size_t>(n) * ncols;
+  cudaEvent_t e0 = h->ev0, e1 = h->ev1;
+  CK(cudaEventRecord(e0, h->stream));
+  CK(cudaMemcpy2DAsync(Bd, n * 8, B, ldb * 8, n * 8, ncols, cudaMemcpyHostToDevice, h->stream));
+  if (use_guess) CK(cudaMemcpy2DAsync(Xd, n * 8, X, ldx * 8, n * 8, ncols, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  const double h2d = ms;
+  if ((rc = solve_multi_device(h, ncols, Bd, n, Xd, n, use_guess, tol, max_iters, iters_out, error_out, info_out, nullptr)))
+    return rc;
+  const double solve_ms = h->last_solve_ms;
+  CK(cudaEventRecord(e0, h->stream));
+  CK(cudaMemcpy2DAsync(X, ldx * 8, Xd, n * 8, n * 8, ncols, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  h->last_h2d_ms = h2d;
+  h->last_d2h_ms = ms;
+  h->last_solve_ms = solve_ms;
+  return 0;
+}
+
 int b200s_get_stats(b200s_handle* h, b200s_stats* out) {
   if (!h || !out) return B200S_ERR_INVALID;
   b200s_stats st;
@@ -1125,6 +1453,7 @@ int b200s_get_stats(b200s_handle* h, b200s_stats* out) {
   st.vec_block = kVecThreads;
   st.loop_mode = h->loop_mode;
   st.evict_first = h->evict_first;
+  st.l2_persist = h->l2_persist;
   st.sm_count = h->sm_count;
   st.last_solve_ms = h->last_solve_ms;
   st.last_h2d_ms = h->last_h2d_ms;

@@ -38,7 +38,7 @@ struct Scalars {
   double rho, rho_old, w, r0_sqnorm, r0v, ts, tt, rho_next, eps2;
   long long restarts;
   int restart;     // this iteration starts with the re-orthogonalisation branch (BiCGSTAB.h:72-81)
-  int pad1;
+  int stop_all;    // multi-column solves: every column's `stop` is set (kept in the first column's block)
   // bookkeeping
   long long spmv_count;
   long long hist_len;

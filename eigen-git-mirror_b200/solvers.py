@@ -345,9 +345,26 @@ class _IterativeSolverBase(SparseOperator):
             x = np.zeros(self._rows, dt) if x0 is None else np.array(x0, dtype=dt, copy=True)
             self._iterations, self._error, self._info = self._solve_vector(np.ascontiguousarray(b), x, x0 is not None)
             return x
-        # multi-column right-hand side: sequential, info = worst, iterations / error = last column (:375-388)
+        # multi-column right-hand side: info = worst, iterations / error = last column (:375-388)
         X = np.zeros(b.shape, dt, order="F") if x0 is None else np.array(x0, dtype=dt, order="F", copy=True)
         global_info = Success
+        if not self._bicg and dt == np.float64 and b.shape[1] > 0:
+            # CG: the columns share one stream of the matrix per iteration (b200s_cg_solve_multi_f64); per-column
+            # results are bit-identical to the sequential loop of the reference
+            Bf = np.asfortranarray(b)
+            nc = b.shape[1]
+            its, errs, infos = np.zeros(nc, np.int64), np.zeros(nc, np.float64), np.zeros(nc, np.int32)
+            self._hd.check(self._hd.L.b200s_cg_solve_multi_f64(
+                self._hd.h, nc, _ptr(Bf), max(1, Bf.shape[0]), _ptr(X), max(1, X.shape[0]), int(x0 is not None),
+                self.tolerance(), self.maxIterations(), _ptr(its), _ptr(errs), _ptr(infos)))
+            self.column_iterations, self.column_errors, self.column_infos = its, errs, infos
+            for info in infos:
+                if info == NumericalIssue:
+                    global_info = NumericalIssue
+                elif info == NoConvergence:
+                    global_info = NoConvergence
+            self._iterations, self._error, self._info = int(its[-1]), float(errs[-1]), global_info
+            return X
         for k in range(b.shape[1]):
             xk = np.ascontiguousarray(X[:, k])
             self._iterations, self._error, info = self._solve_vector(np.ascontiguousarray(b[:, k]), xk, x0 is not None)
@@ -374,6 +391,21 @@ class _IterativeSolverBase(SparseOperator):
                           C.byref(it), C.byref(err), C.byref(info)))
         self._iterations, self._error, self._info = it.value, err.value, info.value
         return x_dev
+
+    def solve_device_multi(self, B_dev, X_dev, ncols: int, ldb: int = 0, ldx: int = 0, use_guess: bool = False):
+        """CG with `ncols` right-hand sides resident in HBM, column-major (leading dimensions default to rows)."""
+        its, errs, infos = np.zeros(ncols, np.int64), np.zeros(ncols, np.float64), np.zeros(ncols, np.int32)
+        self._hd.check(self._hd.L.b200s_cg_solve_multi_device_f64(
+            self._hd.h, ncols, _ptr(B_dev), ldb or self._rows, _ptr(X_dev), ldx or self._rows, int(use_guess),
+            self.tolerance(), self.maxIterations(), _ptr(its), _ptr(errs), _ptr(infos)))
+        self.column_iterations, self.column_errors, self.column_infos = its, errs, infos
+        self._iterations, self._error = int(its[-1]), float(errs[-1])
+        self._info = NoConvergence if (infos == NoConvergence).any() else Success
+        return X_dev
+
+    def multi_rhs_batch(self) -> int:
+        """Columns that share one stream of the matrix per iteration (0: this handle solves column by column)."""
+        return int(self._hd.L.b200s_multi_rhs_batch(self._hd.h))
 
     def timeline(self) -> dict:
         """Device-side timeline of the last solve on this rank (see b200s_get_timeline)."""

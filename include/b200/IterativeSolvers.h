@@ -81,7 +81,11 @@ struct abi {
 };
 template <>
 struct abi<double> {
-  enum { supported = 1 };
+  enum { supported = 1, has_multi = 1 };
+  static int solve_multi(b200s_handle* h, int64_t nc, const double* B, int64_t ldb, double* X, int64_t ldx, int g,
+                         double tol, int64_t mi, int64_t* it, double* err, int* info) {
+    return b200s_cg_solve_multi_f64(h, nc, B, ldb, X, ldx, g, tol, mi, it, err, info);
+  }
   static int factorize(b200s_handle* h, const double* v, int p) { return b200s_factorize_f64(h, v, p); }
   static int spmv(b200s_handle* h, const double* x, double* y) { return b200s_spmv_f64(h, x, y); }
   static int solve(b200s_handle* h, bool bicg, const double* b, double* x, int g, double tol, int64_t mi, int64_t* it,
@@ -92,7 +96,11 @@ struct abi<double> {
 };
 template <>
 struct abi<float> {
-  enum { supported = 1 };
+  enum { supported = 1, has_multi = 0 };
+  static int solve_multi(b200s_handle*, int64_t, const float*, int64_t, float*, int64_t, int, double, int64_t, int64_t*,
+                         double*, int*) {
+    return B200S_ERR_UNSUPPORTED;
+  }
   static int factorize(b200s_handle* h, const float* v, int p) { return b200s_factorize_f32(h, v, p); }
   static int spmv(b200s_handle* h, const float* x, float* y) { return b200s_spmv_f32(h, x, y); }
   static int solve(b200s_handle* h, bool bicg, const float* b, float* x, int g, double tol, int64_t mi, int64_t* it,
@@ -184,6 +192,18 @@ class DeviceSolver {
     error = err;
     info = static_cast<Eigen::ComputationInfo>(inf);
     return true;
+  }
+
+  // CG for all columns of a column-major block at once (b200s_cg_solve_multi_f64)
+  bool solve_multi(Eigen::Index ncols, const Scalar* B, Eigen::Index ldb, Scalar* X, Eigen::Index ldx, bool use_guess,
+                   double tol, Eigen::Index max_iters, std::vector<int64_t>& iters, std::vector<double>& errors,
+                   std::vector<int>& infos) {
+    if (!m_handle) return false;
+    iters.assign(ncols, 0);
+    errors.assign(ncols, 0.0);
+    infos.assign(ncols, 0);
+    return check(abi<Scalar>::solve_multi(m_handle, ncols, B, ldb, X, ldx, use_guess ? 1 : 0, tol, max_iters,
+                                          iters.data(), errors.data(), infos.data()));
   }
 
   // y = A x through b200s_spmv_* (x: cols() entries on one GPU, this rank's rows otherwise; y: this rank's rows)
@@ -344,6 +364,42 @@ class ConjugateGradient : public Eigen::IterativeSolverBase<ConjugateGradient<Ma
     detail::solve_vector<Scalar>(m_dev, false, b, x, static_cast<double>(Base::m_tolerance), Base::maxIterations(),
                                  m_iterations, err, m_info);
     m_error = static_cast<RealScalar>(err);
+  }
+
+  using Base::_solve_with_guess_impl;
+  /** \internal replaces the per-column loop of IterativeSolverBase.h:366-389 for dense multi-column right-hand sides:
+   * all columns share one stream of the matrix per iteration; every column's x, and the iterations() / error() /
+   * info() the loop would leave behind (last column / worst column), are those of the sequential loop. */
+  template <typename Rhs, typename DestDerived>
+  typename Eigen::internal::enable_if<Rhs::ColsAtCompileTime != 1 && DestDerived::ColsAtCompileTime != 1>::type
+  _solve_with_guess_impl(const Rhs& b, Eigen::MatrixBase<DestDerived>& aDest) const {
+    if (!detail::abi<Scalar>::has_multi || m_dev.world() > 1 || b.cols() < 2) {
+      Base::_solve_with_guess_impl(b, aDest);
+      return;
+    }
+    eigen_assert(Base::rows() == b.rows());
+    typedef Eigen::Matrix<Scalar, Eigen::Dynamic, Eigen::Dynamic> Dense;  // column-major, contiguous
+    Dense B = b, X = aDest.derived();
+    const bool guess = (X.array() != Scalar(0)).any();
+    std::vector<int64_t> its;
+    std::vector<double> errs;
+    std::vector<int> infos;
+    m_iterations = Base::maxIterations();
+    m_error = Base::m_tolerance;
+    if (!m_dev.solve_multi(B.cols(), B.data(), B.outerStride(), X.data(), X.outerStride(), guess,
+                           static_cast<double>(Base::m_tolerance), Base::maxIterations(), its, errs, infos)) {
+      m_info = Eigen::InvalidInput;
+      return;
+    }
+    aDest.derived() = X;
+    Eigen::ComputationInfo global_info = Eigen::Success;
+    for (std::size_t k = 0; k < infos.size(); ++k) {  // IterativeSolverBase.h:383-386
+      if (infos[k] == Eigen::NumericalIssue) global_info = Eigen::NumericalIssue;
+      else if (infos[k] == Eigen::NoConvergence) global_info = Eigen::NoConvergence;
+    }
+    m_iterations = static_cast<Eigen::Index>(its.back());
+    m_error = static_cast<RealScalar>(errs.back());
+    m_info = global_info;
   }
 
   const std::string& lastError() const { return m_dev.lastError(); }

@@ -102,6 +102,8 @@ typedef struct {
   int64_t last_restarts;            /* BiCGSTAB: re-orthogonalisation restarts taken by the last solve (BiCGSTAB.h:72-81) */
   int32_t last_nonfinite;           /* CG: the last solve stopped on a non-finite residual norm (outputs as the reference's) */
   int32_t last_comm_error;          /* a bounded device-side wait on a peer expired during the last call */
+  int32_t l2_persist;               /* the CG working set (r, Ap, D^-1, x, p) is marked persisting in L2 */
+  int32_t reserved1;
 } b200s_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------ */
@@ -171,6 +173,23 @@ int b200s_cg_solve_device_f32(b200s_handle* h, const float* b_dev, float* x_dev,
                               int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
 int b200s_bicgstab_solve_device_f32(b200s_handle* h, const float* b_dev, float* x_dev, int use_guess, double tol,
                                     int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);
+
+/* ---- multi-column right-hand sides: IterativeSolverBase::_solve_with_guess_impl, the loop of :366-389 --------------
+ * B and X are column-major (Eigen's dense default) with leading dimensions ldb, ldx >= rows; column k of X receives
+ * the solution for column k of B, and iters_out / error_out / info_out (ncols entries each, optional) what
+ * iterations() / error() / info() would report after solving that column alone.  The reference solves the columns one
+ * after the other (it streams the matrix once per column and iteration); here up to 8 columns share one stream of the
+ * matrix per iteration (SpMM with interleaved operands, one scalar recurrence per column, a converged column is
+ * frozen while the others continue) and every column's result is BIT-IDENTICAL to its single-column solve.  Handles
+ * the batched kernels do not cover (row-partitioned, float, matrices with very irregular rows) solve column by column
+ * inside the same call; b200s_multi_rhs_batch says which (0 = column by column, else the batch width). */
+int b200s_multi_rhs_batch(b200s_handle* h);
+int b200s_cg_solve_multi_f64(b200s_handle* h, int64_t ncols, const double* B, int64_t ldb, double* X, int64_t ldx,
+                             int use_guess, double tol, int64_t max_iters, int64_t* iters_out, double* error_out,
+                             int* info_out);
+int b200s_cg_solve_multi_device_f64(b200s_handle* h, int64_t ncols, const double* B_dev, int64_t ldb, double* X_dev,
+                                    int64_t ldx, int use_guess, double tol, int64_t max_iters, int64_t* iters_out,
+                                    double* error_out, int* info_out);
 
 /* ---- introspection --------------------------------------------------------------------------------------------- */
 int b200s_get_stats(b200s_handle* h, b200s_stats* out /* out->struct_size must be set */);

@@ -30,4 +30,5 @@ for _ in range(2):
 st = s.stats()
 print(args.solver, "n", args.n, "mode", args.loop_mode, "iters", s.iterations(), "error", s.error(), "launches",
       st["last_kernel_launches"], "solve_ms %.3f" % st["last_solve_ms"],
-      "us/iter %.2f" % (1e3 * st["last_solve_ms"] / max(1, s.iterations())), s.timeline())
+      "us/iter %.2f" % (1e3 * st["last_solve_ms"] / max(1, s.iterations())), "l2_persist", st["l2_persist"],
+      "evict_first", st["evict_first"], s.timeline())

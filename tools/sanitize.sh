@@ -1,12 +1,14 @@
 #!/bin/bash
-# compute-sanitizer passes over a small end-to-end run (SpMV, CG, BiCGSTAB through the C ABI) -- run under gpurun.
+# compute-sanitizer passes -- run under gpurun, one GPU.  Logs land in gpurun_out/ and are committed under profiles/.
+#   memcheck : the whole smoke() (every loop mode, including the WHILE graph)
+#   synccheck, racecheck : tools/sanitize_target.py (stream launches + the persistent cooperative kernel; the tools do
+#                          not support device-side cudaGraphSetConditional, which the WHILE-graph mode uses)
 set -x
 mkdir -p gpurun_out
-# synccheck does not support device-side cudaGraphSetConditional (the WHILE-graph solve dies with "unspecified launch
-# failure" under the tool, memcheck is clean on the same run): it is given the stream loop mode, same kernels.
-for tool in memcheck synccheck; do
-  if [ $tool = synccheck ]; then export B200S_LOOP_MODE=3; extra="--num-cuda-barriers 4096"; else extra=""; fi
-  timeout 900 compute-sanitizer --tool $tool $extra --error-exitcode 7 python __graft_entry__.py --smoke > gpurun_out/sanitizer_$tool.log 2>&1
-  echo "$tool rc=$?"
-  tail -4 gpurun_out/sanitizer_$tool.log
-done
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python __graft_entry__.py --smoke > gpurun_out/r2_sanitizer_memcheck.log 2>&1
+echo "memcheck rc=$?" | tee -a gpurun_out/r2_sanitizer_memcheck.log
+timeout 1200 compute-sanitizer --tool synccheck --num-cuda-barriers 4096 --error-exitcode 7 python tools/sanitize_target.py > gpurun_out/r2_sanitizer_synccheck.log 2>&1
+echo "synccheck rc=$?" | tee -a gpurun_out/r2_sanitizer_synccheck.log
+timeout 1800 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 7 python tools/sanitize_target.py > gpurun_out/r2_sanitizer_racecheck.log 2>&1
+echo "racecheck rc=$?" | tee -a gpurun_out/r2_sanitizer_racecheck.log
+tail -5 gpurun_out/r2_sanitizer_*.log
