@@ -290,15 +290,50 @@ def side_config(env, egm, n, solver, dims, steps, warmup, peak):
     return out
 
 
+def multi_rhs_config(env, egm, n, cols, steps, peak):
+    """CG with `cols` right-hand sides at once (the reference solves them one after the other).
+    value = column-iterations per second; every column's result is bit-identical to its single-column solve."""
+    from eigen_git_mirror_b200 import workloads as wl
+    torch = env.torch
+    A = wl.poisson3d(n)
+    S = A.to_scipy()
+    B = torch.from_numpy(np.stack([np.asarray(S @ wl.random_vector(A.rows, 12345 + 7 * k)) for k in range(cols)])).cuda()
+    X = torch.zeros_like(B)
+    s = egm.ConjugateGradient(A, device=env.local_rank)
+    s.setTolerance(TOL)
+    for _ in range(2):
+        s.solve_device_multi(B, X, cols)
+    ms, col_iters = 0.0, 0
+    for _ in range(steps):
+        s.solve_device_multi(B, X, cols)
+        ms += s.stats()["last_solve_ms"]
+        col_iters += int(np.sum(s.column_iterations))
+    N, nnz = A.rows, A.nnz
+    per_pass = (12 * nnz + 4 * (N + 1) + 104 * N * cols)  # one matrix stream + 13 vector passes per column
+    passes = steps * int(np.max(s.column_iterations))
+    gbs = per_pass * passes / (ms * 1e-3) / 1e9
+    out = {"workload": f"3D 7-point Poisson {n}^3, ConjugateGradient<double> + Jacobi, {cols} right-hand sides per solve(B)",
+           "value": col_iters / (ms * 1e-3), "unit": "column-iterations/s", "columns": cols,
+           "batch_width": s.multi_rhs_batch(), "iterations_per_column": s.column_iterations.tolist(),
+           "infos": s.column_infos.tolist(), "ms_per_solve": ms / steps, "bytes_per_batched_iteration": per_pass,
+           "gbs": gbs, "frac_of_hbm": gbs / peak, "gpu_launches": int(s.stats()["last_kernel_launches"])}
+    s.close()
+    del B, X
+    torch.cuda.empty_cache()
+    return out
+
+
 def spmv_sweep(env, egm, rows, peak, reps=20):
     """configs[3]: SpMV-only sweep on synthetic CSR, float and double, device-resident x / y, best of
     3 runs of `reps` back-to-back products after 5 warm-ups; GB/s = algorithmic bytes / time."""
     from eigen_git_mirror_b200 import workloads as wl
     torch = env.torch
-    fams = [("banded_k4", lambda: wl.banded(rows, 4)), ("banded_k16", lambda: wl.banded(rows, 16)),
+    # `rows` for the heavy families; the light ones get 4x the rows so that a product is not launch-bound (a banded
+    # k=4 product over 2^20 rows moves 134 MB: 20 us at the HBM peak, comparable to launch ramp and tail)
+    fams = [("banded_k4", lambda: wl.banded(4 * rows, 4)), ("banded_k16", lambda: wl.banded(4 * rows, 16)),
             ("banded_k50", lambda: wl.banded(rows, 50)), ("banded_k100", lambda: wl.banded(rows, 100)),
             ("stencil27_192", lambda: wl.stencil27(192)),
-            ("powerlaw_m8", lambda: wl.powerlaw(rows, 8)), ("powerlaw_m32", lambda: wl.powerlaw(rows, 32)),
+            ("powerlaw_m8", lambda: wl.powerlaw(4 * rows, 8)), ("powerlaw_m32", lambda: wl.powerlaw(rows, 32)),
             ("powerlaw_m100", lambda: wl.powerlaw(rows, 100)), ("powerlaw_m200", lambda: wl.powerlaw(rows, 200))]
     out = {}
     for name, gen in fams:
@@ -444,6 +479,7 @@ def run_ours(args):
             if world == 1 and solver == "cg" and n == 256:
                 configs["bicgstab_256"] = side_config(env, egm, 256, "bicgstab", 3, max(2, args.steps // 4), 3, peak)
                 configs["poisson2d_1024"] = side_config(env, egm, 1024, "cg", 2, max(2, args.steps // 4), 3, peak)
+                configs["multi_rhs_4"] = multi_rhs_config(env, egm, 256, 4, max(2, args.steps // 4), peak)
                 configs["spmv_sweep"] = spmv_sweep(env, egm, args.sweep_rows, peak)
             if world == 8 and solver == "cg" and n == 256:
                 configs["poisson3d_512"] = side_config(env, egm, 512, "cg", 3, 3, 3, peak)

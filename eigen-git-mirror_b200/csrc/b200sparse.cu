@@ -851,7 +851,10 @@ int solve_multi_device(b200s_handle* h, int64_t ncols, const double* B, int64_t 
     int rc, took;
     h->last_solve_ms = 0;
     if (batched && left >= 2) {
-      const int kmax = std::max(2, std::min(kMultiMax, env_int("B200S_MULTI_K", kMultiMax)));
+      // Measured at 256^3 (profiles/r2_multi_rhs.jsonl): 4 columns per batch run at 0.97 of the HBM roofline of the
+      // batched iteration (1.79x the per-column rate of single solves); 8 per batch are 20 % slower per column
+      // (register pressure, L1 wavefronts of 64-byte rows), so wider blocks are cut into batches of 4.
+      const int kmax = std::max(2, std::min(kMultiMax, env_int("B200S_MULTI_K", 4)));
       if (left >= 5 && kmax >= 8) { took = static_cast<int>(std::min<int64_t>(8, left)); rc = run_solve_multi<8>(h, took, B + c * ldb, ldb, X + c * ldx, ldx, use_guess, tol, max_iters, it, er, in); }
       else if (left >= 3 && kmax >= 4) { took = static_cast<int>(std::min<int64_t>(4, left)); rc = run_solve_multi<4>(h, took, B + c * ldb, ldb, X + c * ldx, ldx, use_guess, tol, max_iters, it, er, in); }
       else { took = 2; rc = run_solve_multi<2>(h, took, B + c * ldb, ldb, X + c * ldx, ldx, use_guess, tol, max_iters, it, er, in); }
@@ -1386,7 +1389,9 @@ B200S_SOLVE_ENTRY(b200s_cg_solve_device_f32, float, solve_device, false)
 B200S_SOLVE_ENTRY(b200s_bicgstab_solve_device_f32, float, solve_device, true)
 #undef B200S_SOLVE_ENTRY
 
-int b200s_multi_rhs_batch(b200s_handle* h) { return (h && multi_supported(h)) ? kMultiMax : 0; }
+int b200s_multi_rhs_batch(b200s_handle* h) {
+  return (h && multi_supported(h)) ? std::max(2, std::min(kMultiMax, env_int("B200S_MULTI_K", 4))) : 0;
+}
 
 int b200s_cg_solve_multi_device_f64(b200s_handle* h, int64_t ncols, const double* B_dev, int64_t ldb, double* X_dev,
                                     int64_t ldx, int use_guess, double tol, int64_t max_iters, int64_t* iters_out,

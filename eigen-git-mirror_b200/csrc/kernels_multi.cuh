@@ -92,14 +92,51 @@ __device__ __forceinline__ void finish_reduction_multi(const MultiArgs<K>& a, do
 // ------------------------------------------------------------------------------------------------ K-wide SpMV
 // y[i][:] = sum_k A[i,k] x[k][:]  (+ per-column dots w.y); same tiles, same lanes per row, same accumulation order
 // per column as tile_rows_reduce.
+// Row access: the K values of a row are contiguous.  K = 2: one 128-bit access; K >= 4: 256-bit accesses (LDG.E.256 /
+// STG.E.256 on sm_100): one instruction per 32-byte sector, so a warp that walks consecutive rows touches every
+// 128-byte line once per instruction -- two 128-bit loads per row would double the L1 wavefronts (measured: the
+// K = 4 product was L1tex-bound that way).
 template <int K>
 __device__ __forceinline__ void ldrow(const double* p, long long row, double (&out)[K]) {
-  const double2* q = reinterpret_cast<const double2*>(p + row * K);
+  const double* q = p + row * K;
+  if (K == 2) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(q));
+    out[0] = t.x;
+    out[1] = t.y;
+  } else {
 #pragma unroll
-  for (int j = 0; j < K / 2; ++j) {
-    const double2 t = __ldg(q + j);
-    out[2 * j] = t.x;
-    out[2 * j + 1] = t.y;
+    for (int j = 0; j < K; j += 4)
+      asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                   : "=d"(out[j]), "=d"(out[j + 1]), "=d"(out[j + 2]), "=d"(out[j + 3])
+                   : "l"(q + j));
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void ldk(const double* p, long long row, double (&out)[K]) {
+  const double* q = p + row * K;
+  if (K == 2) {
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(out[0]), "=d"(out[1]) : "l"(q) : "memory");
+  } else {
+#pragma unroll
+    for (int j = 0; j < K; j += 4)
+      asm volatile("ld.global.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
+                   : "=d"(out[j]), "=d"(out[j + 1]), "=d"(out[j + 2]), "=d"(out[j + 3])
+                   : "l"(q + j)
+                   : "memory");
+  }
+}
+template <int K>
+__device__ __forceinline__ void stk(double* p, long long row, const double (&v)[K]) {
+  double* q = p + row * K;
+  if (K == 2) {
+    *reinterpret_cast<double2*>(q) = make_double2(v[0], v[1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < K; j += 4)
+      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(q + j), "d"(v[j]), "d"(v[j + 1]), "d"(v[j + 2]),
+                   "d"(v[j + 3])
+                   : "memory");
   }
 }
 
@@ -112,7 +149,7 @@ __device__ __forceinline__ void tile_rows_reduce_k(const double* __restrict__ sv
   const int lane = threadIdx.x & (L - 1);
   const int grp = threadIdx.x >> LG;
   constexpr int NGRP = kSpmvThreads >> LG;
-  constexpr int B = (K >= 8) ? 1 : 2;  // entries per lane and trip: B*K gathered doubles in flight per thread
+  constexpr int B = (K >= 8) ? 1 : (K == 4) ? 2 : 4;  // entries per lane and trip: B*K = 8 gathered doubles in flight per thread
   for (int base = 0; base < nrows; base += NGRP) {
     const int r = base + grp;
     double sum[K];
@@ -154,14 +191,12 @@ __device__ __forceinline__ void tile_rows_reduce_k(const double* __restrict__ sv
     if (r < nrows && lane == 0) {
       double wr[K];
       ldrow<K>(w, row0 + r, wr);
-      double2* yo = reinterpret_cast<double2*>(y + static_cast<long long>(row0 + r) * K);
 #pragma unroll
       for (int q = 0; q < K; ++q) {
         sum[q] = add_rn(sum[q], 0.0);  // -0 -> +0 as in the single-column product
         d0[q] = fma_rn(wr[q], sum[q], d0[q]);
       }
-#pragma unroll
-      for (int q = 0; q < K / 2; ++q) yo[q] = make_double2(sum[2 * q], sum[2 * q + 1]);
+      stk<K>(y, row0 + r, sum);
     }
   }
 }
@@ -242,24 +277,6 @@ __device__ __forceinline__ void vec_loop_rows(long long n, FR fr) {
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (long long i = np * 2; i < n; ++i) fr(i);
-}
-
-template <int K>
-__device__ __forceinline__ void ldk(const double* p, long long row, double (&out)[K]) {
-  const double2* q = reinterpret_cast<const double2*>(p + row * K);
-#pragma unroll
-  for (int j = 0; j < K / 2; ++j) {
-    double2 t;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "l"(q + j) : "memory");
-    out[2 * j] = t.x;
-    out[2 * j + 1] = t.y;
-  }
-}
-template <int K>
-__device__ __forceinline__ void stk(double* p, long long row, const double (&v)[K]) {
-  double2* q = reinterpret_cast<double2*>(p + row * K);
-#pragma unroll
-  for (int j = 0; j < K / 2; ++j) q[j] = make_double2(v[2 * j], v[2 * j + 1]);
 }
 
 // ConjugateGradient.h:43-67 for K columns

@@ -178,7 +178,7 @@ int b200s_bicgstab_solve_device_f32(b200s_handle* h, const float* b_dev, float* 
  * B and X are column-major (Eigen's dense default) with leading dimensions ldb, ldx >= rows; column k of X receives
  * the solution for column k of B, and iters_out / error_out / info_out (ncols entries each, optional) what
  * iterations() / error() / info() would report after solving that column alone.  The reference solves the columns one
- * after the other (it streams the matrix once per column and iteration); here up to 8 columns share one stream of the
+ * after the other (it streams the matrix once per column and iteration); here 4 columns at a time share one stream of the
  * matrix per iteration (SpMM with interleaved operands, one scalar recurrence per column, a converged column is
  * frozen while the others continue) and every column's result is BIT-IDENTICAL to its single-column solve.  Handles
  * the batched kernels do not cover (row-partitioned, float, matrices with very irregular rows) solve column by column

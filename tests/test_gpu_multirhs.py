@@ -61,11 +61,14 @@ def _check_batched_equals_sequential(egm, s, B, X0=None):
 
 
 @pytest.mark.parametrize("ncols", [2, 3, 4, 5, 7, 8, 11, 17])
-def test_batched_columns_equal_single_column_solves(ncols, egm):
+@pytest.mark.parametrize("kmax", [2, 4, 8])
+def test_batched_columns_equal_single_column_solves(ncols, kmax, egm, monkeypatch):
+    """Every batch width the library has kernels for (B200S_MULTI_K; 4 is the default, measured fastest)."""
     from eigen_git_mirror_b200 import workloads as wl
+    monkeypatch.setenv("B200S_MULTI_K", str(kmax))
     A = wl.varcoef3d(14)
     s = egm.ConjugateGradient(A)
-    assert s.multi_rhs_batch() == 8
+    assert s.multi_rhs_batch() == kmax
     s.setTolerance(TOL)
     seq = _check_batched_equals_sequential(egm, s, _columns(wl, A, ncols))
     assert len({it for _, it, _, _ in seq}) > 1  # the columns really stop at different iterations
@@ -90,7 +93,7 @@ def test_batched_over_tile_flavours_and_loop_modes(matrix, loop_mode, egm, golde
         S.sort_indices()
         A = wl.CsrMatrix(1500, 1500, S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data)
     s = egm.ConjugateGradient(A, loop_mode=loop_mode, chunk_iters=5)
-    assert s.multi_rhs_batch() == 8
+    assert s.multi_rhs_batch() == 4
     s.setTolerance(TOL)
     _check_batched_equals_sequential(egm, s, _columns(wl, A, 6))
     s.close()
