@@ -12,11 +12,12 @@ Layout
 Importing the package does not load the CUDA library; the first solver / operator does, and raises if it is missing.
 """
 from . import workloads  # noqa: F401
-from .solvers import (BiCGSTAB, Communicator, ConjugateGradient, DiagonalPreconditioner,  # noqa: F401
-                      IdentityPreconditioner, InvalidInput, Lower, NoConvergence, NumericalIssue, SparseOperator,
-                      Success, Upper, device_count, partition_rows)
+from . import solvers  # noqa: F401
+from .solvers import (GMRES, MINRES, BiCGSTAB, Communicator, ConjugateGradient, DiagonalPreconditioner,  # noqa: F401
+                      IdentityPreconditioner, InvalidInput, LeastSquaresConjugateGradient, Lower, NoConvergence,
+                      NumericalIssue, SparseOperator, Success, Upper, device_count, partition_rows)
 from ._lib import B200Error  # noqa: F401
 
-__all__ = ["ConjugateGradient", "BiCGSTAB", "SparseOperator", "Communicator", "partition_rows", "device_count",
+__all__ = ["ConjugateGradient", "BiCGSTAB", "LeastSquaresConjugateGradient", "MINRES", "GMRES", "SparseOperator", "Communicator", "partition_rows", "device_count",
            "Lower", "Upper", "Success", "NumericalIssue", "NoConvergence", "InvalidInput", "DiagonalPreconditioner",
            "IdentityPreconditioner", "B200Error", "workloads"]

@@ -79,6 +79,10 @@ def lib() -> C.CDLL:
     L.b200s_cg_solve_multi_f64.argtypes = multi_args
     L.b200s_cg_solve_multi_device_f64.argtypes = multi_args
     L.b200s_multi_rhs_batch.argtypes = [H]
+    out3 = [C.POINTER(i64), C.POINTER(dbl), C.POINTER(C.c_int)]
+    L.b200s_lscg_solve_f64.argtypes = [H, H, vp, vp, C.c_int, dbl, i64, C.c_int, C.c_int] + out3
+    L.b200s_minres_solve_f64.argtypes = [H, vp, vp, C.c_int, dbl, i64] + out3
+    L.b200s_gmres_solve_f64.argtypes = [H, vp, vp, C.c_int, dbl, i64, i64] + out3
     L.b200s_get_stats.argtypes = [H, C.POINTER(Stats)]
     L.b200s_get_invdiag_f64.argtypes = [H, vp]
     L.b200s_get_timeline.argtypes = [H, vp, C.c_int]

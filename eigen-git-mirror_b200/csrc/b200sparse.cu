@@ -19,6 +19,7 @@
 #include "../../include/b200sparse.h"
 #include "kernels.cuh"
 #include "kernels_multi.cuh"
+#include "kernels_krylov.cuh"
 
 using namespace b200s;
 
@@ -1156,6 +1157,8 @@ int configure_l2_persistence(b200s_handle* h) {
   return 0;
 }
 
+#include "krylov.inc"
+
 }  // namespace
 
 // ================================================================================================ C ABI
@@ -1388,6 +1391,20 @@ B200S_SOLVE_ENTRY(b200s_bicgstab_solve_device_f64, double, solve_device, true)
 B200S_SOLVE_ENTRY(b200s_cg_solve_device_f32, float, solve_device, false)
 B200S_SOLVE_ENTRY(b200s_bicgstab_solve_device_f32, float, solve_device, true)
 #undef B200S_SOLVE_ENTRY
+
+int b200s_lscg_solve_f64(b200s_handle* hA, b200s_handle* hAt, const double* b, double* x, int use_guess, double tol,
+                         int64_t max_iters, int precond, int colmajor_precond, int64_t* iters_out, double* error_out,
+                         int* info_out) {
+  return lscg_solve(hA, hAt, b, x, use_guess, tol, max_iters, precond, colmajor_precond, iters_out, error_out, info_out);
+}
+int b200s_minres_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
+                           int64_t* iters_out, double* error_out, int* info_out) {
+  return minres_solve(h, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);
+}
+int b200s_gmres_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
+                          int64_t restart, int64_t* iters_out, double* error_out, int* info_out) {
+  return gmres_solve(h, b, x, use_guess, tol, max_iters, restart, iters_out, error_out, info_out);
+}
 
 int b200s_multi_rhs_batch(b200s_handle* h) {
   return (h && multi_supported(h)) ? std::max(2, std::min(kMultiMax, env_int("B200S_MULTI_K", 4))) : 0;

@@ -526,6 +526,42 @@ __device__ __forceinline__ void tile_rows_reduce(const T* __restrict__ sv, const
   }
 }
 
+// Phase 2 of the two-phase ("stream") tiles: the products already sit in shared memory, each row only has to be
+// summed.  Kernel selection at ROW granularity from the row length: a short row is summed by one thread (scalar), a
+// longer one by a whole warp (32 lanes + shuffle tree) -- in a tile of 250 short rows and one row of 1,500 entries
+// nobody waits for a single thread walking the long row.  Fixed row-to-thread mapping: deterministic.
+template <typename T>
+__device__ __forceinline__ void tile_rows_reduce_binned(const T* __restrict__ sv, const int32_t* __restrict__ srp,
+                                                        int nrows, int row0, int vb0, T* __restrict__ y, const T* w,
+                                                        double& d0, double& d1) {
+  constexpr int kShortRow = 12;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto finish = [&](int r, T sum) {
+    sum = add_rn(sum, T(0));  // -0 -> +0
+    y[row0 + r] = sum;
+    if (w) d0 = fma_rn(static_cast<double>(w[row0 + r]), static_cast<double>(sum), d0);
+    d1 = fma_rn(static_cast<double>(sum), static_cast<double>(sum), d1);
+  };
+  for (int r = tid; r < nrows; r += kSpmvThreads) {  // scalar bin
+    const int k0 = srp[r], k1 = srp[r + 1];
+    if (k1 - k0 <= kShortRow) {
+      T sum = T(0);
+      for (int k = k0; k < k1; ++k) sum = add_rn(sum, sv[k - vb0]);
+      finish(r, sum);
+    }
+  }
+  for (int r = warp; r < nrows; r += kSpmvThreads / 32) {  // warp bin
+    const int k0 = srp[r], k1 = srp[r + 1];
+    if (k1 - k0 > kShortRow) {
+      T sum = T(0);
+      for (int k = k0 + lane; k < k1; k += 32) sum = add_rn(sum, sv[k - vb0]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum = add_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+      if (lane == 0) finish(r, sum);
+    }
+  }
+}
+
 // Per-CTA state of the staged product.  `seq` counts the tiles this CTA has consumed since the mbarriers were
 // initialised, which fixes the stage (seq % stages) and the barrier parity ((seq / stages) & 1) of every tile, also
 // across successive products inside one persistent kernel.
@@ -658,18 +694,29 @@ __device__ __forceinline__ void spmv_tiles(const SpmvArgs<T>& a, SpmvCta<T>& cx,
       const int cb0 = tl.nnz0 & ~3;
       if (flags & kTileStream) {
         // phase 1: products, perfectly balanced over the CTA (CSR-stream); phase 2 sums them per row
+        // All shared-memory reads and all gathers of a thread are issued before its first store: the stores into sv
+        // could alias the index reads as far as the compiler knows, which would serialise the loop to one gather in
+        // flight per thread.  (A tile holds at most 8 * 256 entries by default; larger tiles take more rounds.)
         const int k1 = tl.nnz0 + tl.nnz;
-        for (int kk = tl.nnz0 + tid; kk < k1; kk += kSpmvThreads)
-          sv[kk - vb0] = mul_rn(sv[kk - vb0], ldx<NC>(a.x + sc[kk - cb0]));
-        __syncthreads();
-        switch (lg) {
-          case 0: tile_rows_reduce<T, 0, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 1: tile_rows_reduce<T, 1, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 2: tile_rows_reduce<T, 2, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 3: tile_rows_reduce<T, 3, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          case 4: tile_rows_reduce<T, 4, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
-          default: tile_rows_reduce<T, 5, true, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, 0, d0, d1); break;
+        for (int k0 = tl.nnz0 + tid; k0 < k1; k0 += 8 * kSpmvThreads) {
+          int c[8];
+          T v[8], xv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int kk = k0 + j * kSpmvThreads;
+            c[j] = (kk < k1) ? sc[kk - cb0] : 0;
+            v[j] = (kk < k1) ? sv[kk - vb0] : T(0);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[j] = (k0 + j * kSpmvThreads < k1) ? ldx<NC>(a.x + c[j]) : T(0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int kk = k0 + j * kSpmvThreads;
+            if (kk < k1) sv[kk - vb0] = mul_rn(v[j], xv[j]);
+          }
         }
+        __syncthreads();
+        tile_rows_reduce_binned<T>(sv, srp, nrows, tl.row0, vb0, a.y, w, d0, d1);
       } else {
         switch (lg) {
           case 0: tile_rows_reduce<T, 0, false, NC>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, w, a.tail_blk, d0, d1); break;

@@ -307,6 +307,19 @@ int build_plan(const b200s_config& cfg, int64_t rows, int64_t cols, int64_t nnz,
     }
   }
   build_tiles(p, row_is_boundary);
+  // Strongly irregular matrices (a quarter or more of the tiles two-phase) are bound by the x gathers, not by the
+  // matrix stream: half-size tiles let more CTAs be resident per SM, which keeps the gather pipe busier while other
+  // CTAs sit in their barriers (measured on power-law rows, profiles/r2_exp_powerlaw.txt: 0.225 -> 0.26 of the HBM
+  // figure).  Only when the caller did not fix the geometry.
+  static const int auto_small = [] { const char* e = std::getenv("B200S_AUTO_SMALL_TILES"); return e ? std::atoi(e) : 1; }();
+  if (auto_small && cfg.tile_nnz <= 0 && p.tile_nnz == kDefaultTileNnz && !p.tiles.empty() &&
+      static_cast<size_t>(p.n_stream) * 4 >= p.tiles.size()) {
+    p.tile_nnz = kDefaultTileNnz / 2;
+    p.n_stream = p.n_long = p.n_boundary_tiles = 0;
+    for (int& b : p.by_lanes) b = 0;
+    p.tiles.clear();
+    build_tiles(p, row_is_boundary);
+  }
   return 0;
 }
 

@@ -439,3 +439,100 @@ class BiCGSTAB(_IterativeSolverBase):
     def __init__(self, A=None, preconditioner: int = DiagonalPreconditioner, comm: Optional[Communicator] = None,
                  **cfg):
         super().__init__(A, Lower | Upper, preconditioner, comm, **cfg)
+
+
+class MINRES(_IterativeSolverBase):
+    """MINRES<SparseMatrix<double>, UpLo, Preconditioner> (unsupported/Eigen/src/IterativeSolvers/MINRES.h:29-262) for
+    self-adjoint operators; the default preconditioner is the identity, as in the reference.  One GPU, double."""
+
+    def __init__(self, A=None, uplo: int = Lower, preconditioner: int = IdentityPreconditioner, **cfg):
+        super().__init__(A, uplo, preconditioner, None, **cfg)
+
+    def _solve_vector(self, b, x, use_guess):
+        it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
+        self._hd.check(self._hd.L.b200s_minres_solve_f64(self._hd.h, _ptr(b), _ptr(x), int(use_guess), self.tolerance(),
+                                                         self.maxIterations(), C.byref(it), C.byref(err), C.byref(info)))
+        return it.value, err.value, info.value
+
+    _bicg = True  # multi-column right-hand sides: the reference's per-column loop
+
+
+class GMRES(_IterativeSolverBase):
+    """GMRES<SparseMatrix<double>, Preconditioner> (unsupported/Eigen/src/IterativeSolvers/GMRES.h:55-325): restarted,
+    Householder Arnoldi; set_restart / get_restart as in the reference (default 30).  One GPU, double."""
+    _bicg = True
+
+    def __init__(self, A=None, preconditioner: int = DiagonalPreconditioner, **cfg):
+        self._restart = 30
+        super().__init__(A, Lower | Upper, preconditioner, None, **cfg)
+
+    def get_restart(self):
+        return self._restart
+
+    def set_restart(self, restart):
+        self._restart = int(restart)
+
+    def _solve_vector(self, b, x, use_guess):
+        it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
+        self._hd.check(self._hd.L.b200s_gmres_solve_f64(self._hd.h, _ptr(b), _ptr(x), int(use_guess), self.tolerance(),
+                                                        self.maxIterations(), self._restart, C.byref(it), C.byref(err),
+                                                        C.byref(info)))
+        return it.value, err.value, info.value
+
+
+class LeastSquaresConjugateGradient(_IterativeSolverBase):
+    """LeastSquaresConjugateGradient<SparseMatrix<double,RowMajor>, Preconditioner>
+    (LeastSquareConjugateGradient.h:26-208): min |A x - b| for a rows x cols matrix.  The transposed matrix needed for
+    A^T r is built once per compute() on the host (scipy) and lives in a second device handle.  preconditioner:
+    DiagonalPreconditioner selects LeastSquareDiagonalPreconditioner (the reference's default), Identity the identity.
+    One GPU, double."""
+    _bicg = True
+
+    def __init__(self, A=None, preconditioner: int = DiagonalPreconditioner, **cfg):
+        self._t = None
+        super().__init__(A, Lower | Upper, preconditioner, None, **cfg)
+
+    def analyzePattern(self, A, inner_nnz=None):
+        A = _as_csr(A)
+        super().analyzePattern(A, inner_nnz)
+        At = A.to_scipy().T.tocsr()
+        At.sort_indices()
+        self._At = CsrMatrix(A.cols, A.rows, _index32(At.indptr, "rowptr"), _index32(At.indices, "colidx"),
+                             np.ascontiguousarray(At.data, dtype=np.float64), 0)
+        if self._t is None:
+            self._t = SparseOperator()
+        self._t.analyzePattern(self._At)
+        return self
+
+    def factorize(self, A, precond=None):
+        A = _as_csr(A)
+        super().factorize(A, IdentityPreconditioner)  # the LS preconditioner is built from A^T inside the solve
+        At = A.to_scipy().T.tocsr()
+        At.sort_indices()
+        self._At = CsrMatrix(A.cols, A.rows, self._At.rowptr, self._At.colidx, np.ascontiguousarray(At.data, np.float64), 0)
+        self._t.factorize(self._At, IdentityPreconditioner)
+        return self
+
+    def maxIterations(self):
+        return 2 * self._cols if self._max_iterations < 0 else self._max_iterations
+
+    def _solve(self, b, x0):
+        if not self._is_initialized:
+            raise AssertionError("solver is not initialized.")
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        if b.ndim != 1 or b.shape[0] != self._rows:
+            raise AssertionError("solve(): invalid number of rows of the right hand side matrix b")
+        x = np.zeros(self._cols) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+        if x.shape != (self._cols,):
+            raise AssertionError("solveWithGuess(): the guess must have cols() entries")
+        it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
+        self._hd.check(self._hd.L.b200s_lscg_solve_f64(self._hd.h, self._t._hd.h, _ptr(b), _ptr(x), int(x0 is not None),
+                                                       self.tolerance(), self.maxIterations(), self._precond, 0,
+                                                       C.byref(it), C.byref(err), C.byref(info)))
+        self._iterations, self._error, self._info = it.value, err.value, info.value
+        return x
+
+    def close(self):
+        if self._t is not None:
+            self._t.close()
+        super().close()

@@ -191,6 +191,28 @@ int b200s_cg_solve_multi_device_f64(b200s_handle* h, int64_t ncols, const double
                                     int64_t ldx, int use_guess, double tol, int64_t max_iters, int64_t* iters_out,
                                     double* error_out, int* info_out);
 
+/* ---- further solvers on the same device primitives (SpMV, fused vector updates, deterministic dots) -------------------
+ * One GPU, double.  The loops are the reference's, statement by statement; vectors stay on the device, the scalar
+ * bookkeeping (Givens / Householder coefficients) runs on the host between kernels.
+ *   lscg   : LeastSquaresConjugateGradient (Eigen/src/IterativeLinearSolvers/LeastSquareConjugateGradient.h:26-93,
+ *            :190-208): min |A x - b| for a rows x cols matrix.  hA holds A, hAt holds A^T (analyze_pattern +
+ *            factorize_f64 on the transposed CSR arrays; any precond value).  b has rows entries, x cols entries.
+ *            precond = 1: LeastSquareDiagonalPreconditioner (BasicPreconditioners.h:127-191), inverse squared column
+ *            norms; colmajor_precond selects which of the reference's two branches defines an empty column
+ *            (0: row-major A -> 0, 1: column-major A -> 1).
+ *   minres : MINRES (unsupported/Eigen/src/IterativeSolvers/MINRES.h:29-140, :236-262) for a self-adjoint operator
+ *            (uplo of analyze_pattern as for CG); preconditioner = the one given to factorize.
+ *   gmres  : restarted GMRES with Householder Arnoldi (unsupported/Eigen/src/IterativeSolvers/GMRES.h:55-212,
+ *            :317-325); restart <= 0 -> 30.  info = NumericalIssue only if the reference's routine would return false.
+ * tol < 0 -> machine epsilon, max_iters < 0 -> 2*cols, as for the other solvers. */
+int b200s_lscg_solve_f64(b200s_handle* hA, b200s_handle* hAt, const double* b, double* x, int use_guess, double tol,
+                         int64_t max_iters, int precond, int colmajor_precond, int64_t* iters_out, double* error_out,
+                         int* info_out);
+int b200s_minres_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
+                           int64_t* iters_out, double* error_out, int* info_out);
+int b200s_gmres_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
+                          int64_t restart, int64_t* iters_out, double* error_out, int* info_out);
+
 /* ---- introspection --------------------------------------------------------------------------------------------- */
 int b200s_get_stats(b200s_handle* h, b200s_stats* out /* out->struct_size must be set */);
 /* Copies the preconditioner's inverse diagonal (this rank's rows) to the host: DiagonalPreconditioner::m_invdiag. */

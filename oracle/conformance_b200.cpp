@@ -16,6 +16,7 @@
 #include "sparse.h"
 
 #include <b200/IterativeSolvers.h>
+#include <b200/KrylovSolvers.h>
 #include <b200/SparseOperator.h>
 
 namespace {
@@ -150,6 +151,42 @@ EIGEN_DECLARE_TEST(b200_bicgstab) {
   CALL_SUBTEST_1((bicgstab_suite<double, int>()));
   CALL_SUBTEST_1((bicgstab_suite<double, long int>()));
   CALL_SUBTEST_1((bicgstab_suite<float, int>()));
+}
+
+// test/lscg.cpp:13-32, unsupported/test/minres.cpp:16-38, unsupported/test/gmres.cpp:13-24 on the b200 classes
+EIGEN_DECLARE_TEST(b200_krylov) {
+  {
+    b200::LeastSquaresConjugateGradient<SparseMatrix<double> > lscg_colmajor_diag;
+    b200::LeastSquaresConjugateGradient<SparseMatrix<double>, IdentityPreconditioner> lscg_colmajor_I;
+    b200::LeastSquaresConjugateGradient<SparseMatrix<double, RowMajor> > lscg_rowmajor_diag;
+    b200::LeastSquaresConjugateGradient<SparseMatrix<double, RowMajor>, IdentityPreconditioner> lscg_rowmajor_I;
+    CALL_SUBTEST_1(check_sparse_square_solving(lscg_colmajor_diag));
+    CALL_SUBTEST_1(check_sparse_square_solving(lscg_colmajor_I));
+    CALL_SUBTEST_1(check_sparse_leastsquare_solving(lscg_colmajor_diag));
+    CALL_SUBTEST_1(check_sparse_leastsquare_solving(lscg_colmajor_I));
+    CALL_SUBTEST_1(check_sparse_square_solving(lscg_rowmajor_diag));
+    CALL_SUBTEST_1(check_sparse_square_solving(lscg_rowmajor_I));
+    CALL_SUBTEST_1(check_sparse_leastsquare_solving(lscg_rowmajor_diag));
+    CALL_SUBTEST_1(check_sparse_leastsquare_solving(lscg_rowmajor_I));
+  }
+  {
+    b200::MINRES<SparseMatrix<double>, Lower, IdentityPreconditioner> minres_colmajor_lower_I;
+    b200::MINRES<SparseMatrix<double>, Upper, IdentityPreconditioner> minres_colmajor_upper_I;
+    b200::MINRES<SparseMatrix<double>, Lower, DiagonalPreconditioner<double> > minres_colmajor_lower_diag;
+    b200::MINRES<SparseMatrix<double>, Upper, DiagonalPreconditioner<double> > minres_colmajor_upper_diag;
+    b200::MINRES<SparseMatrix<double>, Lower | Upper, DiagonalPreconditioner<double> > minres_colmajor_uplo_diag;
+    CALL_SUBTEST_1(check_sparse_spd_solving(minres_colmajor_lower_I));
+    CALL_SUBTEST_1(check_sparse_spd_solving(minres_colmajor_upper_I));
+    CALL_SUBTEST_1(check_sparse_spd_solving(minres_colmajor_lower_diag));
+    CALL_SUBTEST_1(check_sparse_spd_solving(minres_colmajor_upper_diag));
+    CALL_SUBTEST_1(check_sparse_spd_solving(minres_colmajor_uplo_diag));
+  }
+  {
+    b200::GMRES<SparseMatrix<double>, DiagonalPreconditioner<double> > gmres_colmajor_diag;
+    b200::GMRES<SparseMatrix<double, RowMajor>, DiagonalPreconditioner<double> > gmres_rowmajor_diag;
+    CALL_SUBTEST_1(check_sparse_square_solving(gmres_colmajor_diag));
+    CALL_SUBTEST_1(check_sparse_square_solving(gmres_rowmajor_diag));
+  }
 }
 
 EIGEN_DECLARE_TEST(b200_sparse_operator) {

@@ -164,6 +164,13 @@ class Ref:
             getattr(L, f"eigref_bicgstab_{sfx}").argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, fp, fp, fp, C.c_int,
                                                             C.c_double, C.c_int64, C.c_int, C.c_int, ip64, dp, ip, dp,
                                                             dp]
+        if hasattr(L, "eigref_lscg_f64"):
+            L.eigref_lscg_f64.argtypes = [C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int,
+                                          C.c_double, C.c_int64, C.c_int, ip64, dp, ip]
+            L.eigref_minres_f64.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int, C.c_double,
+                                            C.c_int64, C.c_int, C.c_int, ip64, dp, ip]
+            L.eigref_gmres_f64.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int, C.c_double,
+                                           C.c_int64, C.c_int64, C.c_int, ip64, dp, ip]
         L.eigref_symv_f64.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int]
         L.eigref_jacobi_f64.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p]
 
@@ -217,6 +224,28 @@ class Ref:
     def bicgstab(self, A, b, x0=None, tol=-1.0, max_iters=-1, precond=JACOBI, threads=1):
         return self._solve(getattr(self.lib, f"eigref_bicgstab_{self._sfx(A.vals)}"), A, b, x0, tol, max_iters,
                            (precond,), threads)
+
+    def _krylov(self, fn, A, b, x0, ncols_x, args):
+        x = np.zeros(ncols_x) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+        it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
+        rc = fn(*args(np.ascontiguousarray(b, np.float64), x), C.byref(it), C.byref(err), C.byref(info))
+        assert rc == 0
+        return x, it.value, err.value, info.value
+
+    def lscg(self, A, b, x0=None, tol=-1.0, max_iters=-1, precond=JACOBI):
+        return self._krylov(self.lib.eigref_lscg_f64, A, b, x0, A.cols,
+                            lambda bb, x: (A.rows, A.cols, A.nnz, A.rowptr, A.colidx, A.vals, bb, x, int(x0 is not None),
+                                           tol, max_iters, precond))
+
+    def minres(self, A, b, x0=None, tol=-1.0, max_iters=-1, uplo=LOWER, precond=IDENTITY):
+        return self._krylov(self.lib.eigref_minres_f64, A, b, x0, A.rows,
+                            lambda bb, x: (A.rows, A.nnz, A.rowptr, A.colidx, A.vals, bb, x, int(x0 is not None), tol,
+                                           max_iters, uplo, precond))
+
+    def gmres(self, A, b, x0=None, tol=-1.0, max_iters=-1, restart=30, precond=JACOBI):
+        return self._krylov(self.lib.eigref_gmres_f64, A, b, x0, A.rows,
+                            lambda bb, x: (A.rows, A.nnz, A.rowptr, A.colidx, A.vals, bb, x, int(x0 is not None), tol,
+                                           max_iters, restart, precond))
 
 
 _port = None

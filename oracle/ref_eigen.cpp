@@ -7,6 +7,8 @@
 //   ConjugateGradient<...>                   Eigen/src/IterativeLinearSolvers/ConjugateGradient.h:157-225
 //   BiCGSTAB<...>                            Eigen/src/IterativeLinearSolvers/BiCGSTAB.h:157-208
 //   DiagonalPreconditioner / Identity        Eigen/src/IterativeLinearSolvers/BasicPreconditioners.h:35-108,200-222
+//   LeastSquaresConjugateGradient            Eigen/src/IterativeLinearSolvers/LeastSquareConjugateGradient.h
+//   MINRES / GMRES                           unsupported/Eigen/src/IterativeSolvers/MINRES.h, GMRES.h
 // on caller-owned CSR arrays bound zero-copy through Map<const SparseMatrix> (SparseMap.h:270).
 //
 // Used for (1) pinning the C restatement in oracle/oracle.c, (2) generating tests/golden/*,
@@ -14,6 +16,8 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may load this library.
 #include <Eigen/Sparse>
 #include <Eigen/IterativeLinearSolvers>
+#include <iostream>  // the unsupported module header uses std::cerr without including it
+#include <unsupported/Eigen/IterativeSolvers>
 #include <chrono>
 #include <cstdint>
 #ifdef _OPENMP
@@ -216,6 +220,72 @@ int eigref_bicgstab_f32(int64_t n, int64_t nnz, const int* rowptr, const int* co
                         int threads, int64_t* iters, double* error, int* info, double* t_setup, double* t_solve) {
   return bicgstab_dispatch<float>(n, nnz, rowptr, colidx, vals, b, x, use_guess, tol, max_iters, precond, threads,
                                   iters, error, info, t_setup, t_solve);
+}
+
+// ---- LSCG (rows x cols matrix), MINRES, GMRES -------------------------------------------------
+int eigref_lscg_f64(int64_t rows, int64_t cols, int64_t nnz, const int* rowptr, const int* colidx, const double* vals,
+                    const double* b, double* x, int use_guess, double tol, int64_t max_iters, int precond,
+                    int64_t* iters, double* error, int* info) {
+  CsrMap<double> A(rows, cols, nnz, rowptr, colidx, vals);
+  Map<const Vec<double>> bm(b, rows);
+  Map<Vec<double>> xm(x, cols);
+  Vec<double> sol;
+#define EIGREF_LSCG(PRE)                                                        \
+  {                                                                             \
+    LeastSquaresConjugateGradient<Csr<double>, PRE> s;                          \
+    s.compute(A);                                                               \
+    if (tol >= 0) s.setTolerance(tol);                                          \
+    if (max_iters >= 0) s.setMaxIterations(max_iters);                          \
+    if (use_guess) { Vec<double> g = xm; sol = s.solveWithGuess(bm, g); }       \
+    else sol = s.solve(bm);                                                     \
+    xm = sol;                                                                   \
+    *iters = s.iterations(); *error = s.error(); *info = int(s.info());         \
+    return 0;                                                                   \
+  }
+  if (precond == 1) EIGREF_LSCG(LeastSquareDiagonalPreconditioner<double>)
+  if (precond == 0) EIGREF_LSCG(IdentityPreconditioner)
+#undef EIGREF_LSCG
+  return -1;
+}
+
+int eigref_minres_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals, const double* b,
+                      double* x, int use_guess, double tol, int64_t max_iters, int uplo, int precond, int64_t* iters,
+                      double* error, int* info) {
+  CsrMap<double> A(n, n, nnz, rowptr, colidx, vals);
+  double ts, tv;
+#define EIGREF_MINRES(UPLO, PRE)                                                                       \
+  {                                                                                                    \
+    MINRES<Csr<double>, UPLO, PRE> s;                                                                  \
+    return run_solver(s, A, n, b, x, use_guess, tol, max_iters, iters, error, info, &ts, &tv);         \
+  }
+  if (precond == 0) {
+    if (uplo == (Lower | Upper)) EIGREF_MINRES(Lower | Upper, IdentityPreconditioner)
+    if (uplo == Lower) EIGREF_MINRES(Lower, IdentityPreconditioner)
+    if (uplo == Upper) EIGREF_MINRES(Upper, IdentityPreconditioner)
+  } else if (precond == 1) {
+    if (uplo == (Lower | Upper)) EIGREF_MINRES(Lower | Upper, DiagonalPreconditioner<double>)
+    if (uplo == Lower) EIGREF_MINRES(Lower, DiagonalPreconditioner<double>)
+    if (uplo == Upper) EIGREF_MINRES(Upper, DiagonalPreconditioner<double>)
+  }
+#undef EIGREF_MINRES
+  return -1;
+}
+
+int eigref_gmres_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals, const double* b,
+                     double* x, int use_guess, double tol, int64_t max_iters, int64_t restart, int precond,
+                     int64_t* iters, double* error, int* info) {
+  CsrMap<double> A(n, n, nnz, rowptr, colidx, vals);
+  double ts, tv;
+  if (precond == 1) {
+    GMRES<Csr<double>, DiagonalPreconditioner<double>> s;
+    if (restart > 0) s.set_restart(restart);
+    return run_solver(s, A, n, b, x, use_guess, tol, max_iters, iters, error, info, &ts, &tv);
+  } else if (precond == 0) {
+    GMRES<Csr<double>, IdentityPreconditioner> s;
+    if (restart > 0) s.set_restart(restart);
+    return run_solver(s, A, n, b, x, use_guess, tol, max_iters, iters, error, info, &ts, &tv);
+  }
+  return -1;
 }
 
 }  // extern "C"

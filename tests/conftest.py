@@ -31,11 +31,12 @@ class _Files:
 
 
 class Golden:
-    """tests/golden/golden_v1.npz + golden_v2.npz: outputs of the unmodified reference (see tests/golden/make_golden.py
-    and make_golden_v2.py)."""
+    """tests/golden/golden_v{1,2,3}.npz: outputs of the unmodified reference (see tests/golden/make_golden.py,
+    make_golden_v2.py, make_golden_v3.py)."""
 
     def __init__(self):
-        self.z = _Files([os.path.join(ROOT, "tests", "golden", f) for f in ("golden_v1.npz", "golden_v2.npz")])
+        self.z = _Files([os.path.join(ROOT, "tests", "golden", f)
+                         for f in ("golden_v1.npz", "golden_v2.npz", "golden_v3.npz")])
         self.keys = list(self.z.keys())
 
     def cases(self, prefix):
