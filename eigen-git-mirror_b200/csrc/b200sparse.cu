@@ -78,7 +78,8 @@ struct b200s_handle {
   int spmv_grid = 0, spmv_stages = 0, spmv_stages_f32 = 0, spmv_smem = 0, vec_grid = 0;
   int spmv_grid_f32 = 0, spmv_smem_f32 = 0;  // float tiles are smaller: more CTAs fit per SM
   int evict_first = 0;
-  int pdl = 0;           // programmatic dependent launch between the solver kernels (B200S_PDL=1)
+  int pdl = 0;           // programmatic dependent launch between the solver kernels (B200S_PDL, default on)
+  int early_x = 0;       // cg_direction applies x += alpha p before its grid dependency resolves (see kernels.cuh)
   int body_unroll = 1;   // iterations per WHILE-body (amortises the loop-back, keeps PDL edges inside the body)
   GraphSet cg, bicg;
   // multi-column CG (kernels_multi.cuh): interleaved [rows][K] vectors, one control block per column
@@ -374,7 +375,8 @@ int enqueue_cg_body(b200s_handle* h, bool set_cond, cudaGraphConditionalHandle c
   VecArgsT<T> u = make_vec<T>(h, kEpiCgUpdate, kGateLoop, set_cond, cond);
   LAUNCH_VEC(cg_update_kernel<T>, u);
   VecArgsT<T> d = make_vec<T>(h, kEpiNone, kGateNone, false, 0);
-  CK(launch_k(h, cg_direction_kernel<T>, h->vec_grid, kVecThreads, 0, d, h->gridbar.as<unsigned>() + 64));
+  CK(launch_k(h, cg_direction_kernel<T>, h->vec_grid, kVecThreads, 0, d, h->gridbar.as<unsigned>() + 64,
+              (h->pdl && h->early_x) ? 1 : 0));
   h->last_launches++;
   return 0;
 }
@@ -1087,8 +1089,11 @@ int configure_spmv(b200s_handle* h) {
     h->persist_grid_f32 = std::max(1, std::min(h->sm_count * std::max(1, pocc32), kMaxGrid));
   }
   int64_t n2 = std::max<int64_t>(1, p.rows / 2);
-  int64_t vg = std::min<int64_t>(static_cast<int64_t>(h->sm_count) * env_int("B200S_VEC_CTAS_PER_SM", 6),
-                                 (n2 + kVecThreads - 1) / kVecThreads);
+  // CTAs per SM of the fused vector kernels: 6 for HBM-sized vectors; 4 below ~4M rows, where the vectors are (partly)
+  // L2-resident and the ticket / fold tail of the reduction weighs more than bytes in flight (profiles/r2_exp_vec_grid.txt:
+  // 128^3 73.1 -> 70.5 us per iteration, 2D 1024^2 46.3 -> 42.5; 256^3 503 -> 535 the other way).
+  const int vec_ctas = env_int("B200S_VEC_CTAS_PER_SM", p.rows < 4000000 ? 4 : 6);
+  int64_t vg = std::min<int64_t>(static_cast<int64_t>(h->sm_count) * vec_ctas, (n2 + kVecThreads - 1) / kVecThreads);
   h->vec_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(vg, kMaxGrid)));
   // L2 policy of the matrix stream (TMA cache hint).  The matrix is read once per product; everything else (x gathers,
   // the vectors the next kernels read) profits from staying in L2.  Measured:
@@ -1108,8 +1113,26 @@ int configure_spmv(b200s_handle* h) {
     else
       h->evict_first = (l2 > 0 && vec_bytes <= 1.75 * l2 && !all_fits) ? 1 : 0;
   }
-  if (h->loop_auto)
-    h->loop_mode = (p.world > 1 || p.rows >= (int64_t(1) << 22)) ? B200S_LOOP_PERSISTENT : B200S_LOOP_WHILE_GRAPH;
+  // Early x update (cg_direction_kernel): it splits the direction pass in two, so p is read twice.  That is free while
+  // the CG vectors live in L2 (strong scaling: 256^3 over 8 GPUs = 2.1 M rows per GPU; one GPU 128^3: 76.7 -> 74.8 us per
+  // iteration) and costs a full extra HBM pass otherwise (one GPU 256^3: 503 -> 539 us), so it is tied to the size.
+  {
+    int l2 = 0;
+    CK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
+    const double six_vectors = 6.0 * 8.0 * static_cast<double>(p.rows + static_cast<int64_t>(p.ghost_cols.size()));
+    const int want = env_int("B200S_EARLY_X", -1);
+    h->early_x = want >= 0 ? want : (l2 > 0 && six_vectors <= 1.0 * l2 ? 1 : 0);
+  }
+  // AUTO: the WHILE graph everywhere.  Round 1 picked
+  // the persistent kernel for >= 4M rows on one GPU as well (524 vs 544 us per iteration at 256^3); since the SpMV
+  // fetches its tile descriptors a round ahead the stand-alone kernel runs at 250 us (1.06 of the measured copy
+  // bandwidth) and the graph wins: 500.6 vs 516.3 us per iteration, same box (profiles/r2_exp_descriptor_prefetch.txt).
+  if (h->loop_auto) {
+    // ... and on 8 GPUs the graph wins as well since then: 256^3 11,740 vs 10,890 it/s, 512^3 1,963 vs 1,879 it/s
+    // (profiles/r2_exp_loop_mode_x8.txt).  The persistent kernel stays available (B200S_LOOP_PERSISTENT).
+    const int mg = env_int("B200S_LOOP_MODE_MULTI", B200S_LOOP_WHILE_GRAPH);
+    h->loop_mode = (p.world > 1) ? mg : B200S_LOOP_WHILE_GRAPH;
+  }
   // direct kernel: lanes per row from the global mean row length
   int mean = p.rows ? static_cast<int>((p.nnz + p.rows - 1) / p.rows) : 1;
   int lg = 0;
@@ -1224,18 +1247,17 @@ int b200s_create(const b200s_config* cfg, b200s_handle** out) {
     return B200S_ERR_CUDA;
   }
   std::memset(h->hS, 0, sizeof(Scalars));
-  // AUTO: the persistent cooperative kernel drives CG in row-partitioned runs and on one GPU for large problems
-  // (>= 4M rows per GPU); small single-GPU problems and BiCGSTAB use the WHILE graph.  Measured with identical
-  // results (profiles/r1_loop_overheads.txt): 8xB200 512^3 582 -> 539 us per iteration, 256^3 88.4 -> 87.2;
-  // one GPU 256^3 544 -> 524; one GPU 128^3 82.9 (WHILE) vs 86.4.
+  // AUTO resolves to the WHILE graph (see configure_spmv for the measurements behind that; round 1 resolved to the
+  // persistent cooperative kernel for row-partitioned and large problems, profiles/r1_loop_overheads.txt).
   h->loop_mode = h->cfg.loop_mode ? h->cfg.loop_mode : env_int("B200S_LOOP_MODE", B200S_LOOP_AUTO);
   h->loop_auto = (h->loop_mode == B200S_LOOP_AUTO);
-  if (h->loop_auto) h->loop_mode = (h->cfg.world > 1) ? B200S_LOOP_PERSISTENT : B200S_LOOP_WHILE_GRAPH;
+  if (h->loop_auto) h->loop_mode = B200S_LOOP_WHILE_GRAPH;  // refined per problem in configure_spmv
   h->spmv_impl = h->cfg.spmv_impl ? h->cfg.spmv_impl : env_int("B200S_SPMV_IMPL", B200S_SPMV_STAGED);
   h->evict_first = env_int("B200S_EVICT_FIRST", -1);  // -1: decided per problem in configure_spmv
-  // measured (profiles/r1_loop_overheads.txt): PDL with an early trigger lets dependent CTAs squat on registers and
-  // shared memory and slows the 256^3 iteration by 7 %; it only pays below 64^3.  Off by default.
-  h->pdl = env_int("B200S_PDL", 0);
+  // Programmatic dependent launch between the solver kernels.  Round 1's early trigger (at kernel entry) cost 7 % at
+  // 256^3 and was off; the trigger now fires when a CTA's streaming work is done, which is neutral by itself
+  // (profiles/r2_exp_pdl.txt) and lets cg_direction apply x += alpha p behind cg_update's cross-rank all-reduce.
+  h->pdl = env_int("B200S_PDL", 1);
   h->body_unroll = std::max(1, std::min(16, env_int("B200S_BODY_UNROLL", 4)));
   h->comm_timeout_ms = std::max(1, env_int("B200S_COMM_TIMEOUT_MS", 20000));
   if (h->cfg.tile_nnz <= 0) h->cfg.tile_nnz = env_int("B200S_TILE_NNZ", 0);

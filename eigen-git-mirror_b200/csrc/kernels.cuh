@@ -69,7 +69,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   return p;
 }
 // Programmatic dependent launch: let the next kernel of the stream become resident early / wait until everything the
-// previous kernel wrote is visible.  Both are no-ops for launches without the PDL attribute.
+// previous kernel wrote is visible.  Both are no-ops for launches without the PDL attribute.  The trigger is issued
+// LATE -- by each CTA when its streaming work is done, just before the reduction tail -- so that the next kernel's
+// CTAs move in while the last CTA folds the partials and runs the scalar epilogue (and the SpMV's CTAs already
+// prefetch their first tiles), but never squat on an SM whose current CTAs are still streaming (a trigger at kernel
+// entry, round 1, cost 7 % at 256^3).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -596,9 +600,14 @@ __device__ __forceinline__ void spmv_cta_init(const SpmvArgs<T>& a, SpmvCta<T>& 
 
 // One elected thread: start the bulk copies of tile t into stage s (values, column indices, row-pointer slice).
 template <typename T>
+__device__ __forceinline__ void spmv_issue_tile(const SpmvArgs<T>& a, const SpmvCta<T>& cx, const Tile tl, int s);
+template <typename T>
 __device__ __forceinline__ void spmv_issue(const SpmvArgs<T>& a, const SpmvCta<T>& cx, int t, int s) {
+  spmv_issue_tile<T>(a, cx, a.tiles[t], s);
+}
+template <typename T>
+__device__ __forceinline__ void spmv_issue_tile(const SpmvArgs<T>& a, const SpmvCta<T>& cx, const Tile tl, int s) {
   constexpr int VA = 16 / sizeof(T);  // elements per 16-byte unit of the value array
-  const Tile tl = a.tiles[t];
   uint64_t* bar = &cx.full_bar[s];
   if ((tl.meta >> 24) & kTileLong) { mbar_arrive(bar); return; }
   const int nrows = tl.meta & 0xFFFF;
@@ -640,13 +649,21 @@ __device__ __forceinline__ void spmv_tiles(const SpmvArgs<T>& a, SpmvCta<T>& cx,
   const T* w = (NDOT >= 1) ? (a.w ? a.w : a.x) : nullptr;
   bool halo_ready = (a.recv_mask == 0);
   int k = 0;
+  // Tile descriptors are fetched one round ahead (and, by the issuing thread, S rounds ahead): a descriptor load is
+  // an L2 round trip that would otherwise sit in front of every tile -- a larger share of a float tile, which drains
+  // in two thirds of the time of a double tile.
+  Tile tl_next = (static_cast<int>(blockIdx.x) < a.ntiles) ? a.tiles[blockIdx.x] : Tile{};
   for (;; ++k) {
     const int t = blockIdx.x + k * G;
     if (t >= a.ntiles) break;
     const unsigned q = cx.seq + k;
     const int s = q % S;
     const unsigned parity = (q / S) & 1;
-    const Tile tl = a.tiles[t];
+    const Tile tl = tl_next;
+    if (t + G < a.ntiles) tl_next = a.tiles[t + G];
+    const bool refill = (tid == 0) && (t + S * G < a.ntiles);
+    Tile tl_refill = tl;
+    if (refill) tl_refill = a.tiles[t + S * G];
     const int flags = (tl.meta >> 24) & 0xFF;
     const int nrows = tl.meta & 0xFFFF;
     const int lg = (tl.meta >> 16) & 0xFF;
@@ -729,10 +746,7 @@ __device__ __forceinline__ void spmv_tiles(const SpmvArgs<T>& a, SpmvCta<T>& cx,
       }
     }
     __syncthreads();  // every thread is done with stage s
-    if (tid == 0) {
-      const int t2 = t + S * G;
-      if (t2 < a.ntiles) spmv_issue(a, cx, t2, s);
-    }
+    if (refill) spmv_issue_tile<T>(a, cx, tl_refill, s);
   }
   cx.seq += k;
 }
@@ -745,7 +759,6 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
   __shared__ T long_scratch[32];
   // Prologue that does not depend on the previous kernel: barrier setup and the first tile copies (matrix data is
   // constant).  It overlaps the predecessor's tail under programmatic dependent launch.
-  pdl_launch_dependents();
   SpmvCta<T> cx;
   spmv_cta_init(a, cx, smem, full_bar, long_scratch);
   spmv_prefetch(a, cx);
@@ -764,12 +777,15 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
   if (a.red.epilogue != kEpiNone) {
     if (NDOT == 0) {
       double v[1] = {0.0};
+      pdl_launch_dependents();
       finish_reduction<1, kSpmvThreads>(a.red, v, red_scratch, a.history);
     } else if (NDOT == 1) {
       double v[1] = {d0};
+      pdl_launch_dependents();
       finish_reduction<1, kSpmvThreads>(a.red, v, red_scratch, a.history);
     } else {
       double v[2] = {d0, d1};
+      pdl_launch_dependents();
       finish_reduction<2, kSpmvThreads>(a.red, v, red_scratch, a.history);
     }
   }
@@ -780,7 +796,6 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_staged_kernel(const SpmvArg
 template <typename T, int LG, int NDOT>
 __global__ void __launch_bounds__(kSpmvThreads) spmv_direct_kernel(const SpmvArgs<T> a, int rows) {
   __shared__ double red_scratch[32 * 2];
-  pdl_launch_dependents();
   pdl_wait();
   if (gated_out(a.red.S, a.red.gate)) return;
   constexpr int L = 1 << LG;
@@ -813,9 +828,11 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_direct_kernel(const SpmvArg
   if (a.red.epilogue != kEpiNone) {
     if (NDOT <= 1) {
       double v[1] = {NDOT ? d0 : 0.0};
+      pdl_launch_dependents();
       finish_reduction<1, kSpmvThreads>(a.red, v, red_scratch, a.history);
     } else {
       double v[2] = {d0, d1};
+      pdl_launch_dependents();
       finish_reduction<2, kSpmvThreads>(a.red, v, red_scratch, a.history);
     }
   }
@@ -945,7 +962,6 @@ __device__ __forceinline__ void vec_loop(long long n, FP fp, F1 f1) {
 // p = D^-1 r, and the three reductions ||b||^2, ||r||^2, r.p in the same pass.
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const VecArgsT<T> a) {
-  pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32 * 3];
   const bool guess = a.red.S->use_guess != 0;
@@ -973,6 +989,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const VecArgsT<T> 
       if (!guess) a.x[i] = T(0);
       a.r[i] = r; a.p[i] = p;
     });
+  pdl_launch_dependents();
   finish_reduction<3, kVecThreads>(a.red, v, scratch, a.history);
 }
 
@@ -1006,22 +1023,22 @@ __device__ __forceinline__ void cg_update_body(const VecArgsT<T>& av, const T al
 
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) cg_update_kernel(const VecArgsT<T> a) {
-  pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32 * 2];
   if (gated_out(a.red.S, a.red.gate)) return;
   double v[2] = {0.0, 0.0};
   cg_update_body<T>(a, static_cast<T>(a.red.S->alpha), v);
+  pdl_launch_dependents();
   finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
 }
 
 // CG :74 (deferred) and :81,:86: x += alpha p, then -- unless the loop has just stopped -- p = D^-1 r + beta p
+enum { kDirBoth = 0, kDirXOnly = 1, kDirPOnly = 2 };
 template <typename T>
-__device__ __forceinline__ void cg_direction_body(const VecArgsT<T>& av, const T alpha, const T beta,
-                                                  const bool update_p) {
+__device__ __forceinline__ void cg_direction_body(const VecArgsT<T>& av, const T alpha, const T beta, const int what) {
   struct { T* __restrict__ x; T* __restrict__ p; const T* __restrict__ r; const T* __restrict__ invdiag; } a = {
       av.x, av.p, av.r, av.invdiag};
-  if (update_p) {
+  if (what == kDirBoth) {
     vec_loop<T>(av.n,
       [&](long long ip) {
         const Pack<T> r = ldp(a.r, ip), d = ldp(a.invdiag, ip);
@@ -1038,7 +1055,7 @@ __device__ __forceinline__ void cg_direction_body(const VecArgsT<T>& av, const T
         a.x[i] = fma_rn(alpha, p, a.x[i]);
         a.p[i] = fma_rn(beta, p, a.invdiag[i] * a.r[i]);
       });
-  } else {
+  } else if (what == kDirXOnly) {
     vec_loop<T>(av.n,
       [&](long long ip) {
         const Pack<T> p = ldp(a.p, ip);
@@ -1048,18 +1065,43 @@ __device__ __forceinline__ void cg_direction_body(const VecArgsT<T>& av, const T
         stp(a.x, ip, x);
       },
       [&](long long i) { a.x[i] = fma_rn(alpha, a.p[i], a.x[i]); });
+  } else {
+    vec_loop<T>(av.n,
+      [&](long long ip) {
+        const Pack<T> r = ldp(a.r, ip), d = ldp(a.invdiag, ip);
+        Pack<T> p = ldp(a.p, ip);
+#pragma unroll
+        for (int j = 0; j < Pack<T>::N; ++j) p.v[j] = fma_rn(beta, p.v[j], d.v[j] * r.v[j]);
+        stp(a.p, ip, p);
+      },
+      [&](long long i) { a.p[i] = fma_rn(beta, a.p[i], a.invdiag[i] * a.r[i]); });
   }
 }
 
 // Runs after every cg_update: applies the pending x update exactly once (n_update counts updates, n_xapplied the
 // ones already folded into x; launches that find nothing pending -- gated copies after the stop -- do nothing).
+//
+// Under programmatic dependent launch (early_x) the CTAs of this kernel become resident while the last CTA of
+// cg_update is still folding the partials and exchanging {||r||^2, r.z} with the other ranks (4-5 us per iteration on
+// 8 GPUs).  x += alpha p needs nothing from that reduction -- alpha dates from the product before, x and p are not
+// touched by cg_update -- so it is done BEFORE griddepcontrol.wait, hidden behind the all-reduce; only p = z + beta p
+// waits for beta.  The early part runs only when the loop was live when cg_update started (stop == 0): then cg_update
+// is not gated off and this iteration's x update is owed for certain.  Same operation on the same operands: x is
+// bit-identical either way.
 template <typename T>
-__global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgsT<T> a, unsigned int* ticket) {
-  pdl_launch_dependents();
-  pdl_wait();
+__global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgsT<T> a, unsigned int* ticket, int early_x) {
+  __shared__ int s_early;
   const Scalars* S = a.red.S;
-  if (S->n_update == S->n_xapplied) return;
-  cg_direction_body<T>(a, static_cast<T>(S->alpha), static_cast<T>(S->beta), S->stop == 0);
+  if (threadIdx.x == 0) s_early = early_x && (__ldcg(&S->stop) == 0);
+  __syncthreads();
+  const bool early = s_early != 0;
+  if (early) cg_direction_body<T>(a, static_cast<T>(__ldcg(&S->alpha)), T(0), kDirXOnly);
+  pdl_wait();
+  if (__ldcg(&S->n_update) == __ldcg(&S->n_xapplied)) return;
+  const bool update_p = __ldcg(&S->stop) == 0;
+  const T alpha = static_cast<T>(__ldcg(&S->alpha)), beta = static_cast<T>(__ldcg(&S->beta));
+  if (!early) cg_direction_body<T>(a, alpha, beta, update_p ? kDirBoth : kDirXOnly);
+  else if (update_p) cg_direction_body<T>(a, alpha, beta, kDirPOnly);
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(ticket, 1u);
@@ -1074,7 +1116,6 @@ __global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(const VecArgs
 // BiCGSTAB start (BiCGSTAB.h:42-46): r = b - A x0 (t holds A x0), r0 = r, ||b||^2, ||r||^2; v = p = 0 (:56)
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) bicg_init_kernel(const VecArgsT<T> a) {
-  pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32 * 2];
   const bool guess = a.red.S->use_guess != 0;
@@ -1102,13 +1143,13 @@ __global__ void __launch_bounds__(kVecThreads) bicg_init_kernel(const VecArgsT<T
       a.r[i] = r; a.r0[i] = r; a.q[i] = T(0); a.p[i] = T(0);
       v[0] = dacc(b, b, v[0]); v[1] = dacc(r, r, v[1]);
     });
+  pdl_launch_dependents();
   finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
 }
 
 // BiCGSTAB restart (:75-77): r = b - A x (t holds A x), r0 = r, ||r||^2
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) bicg_restart_kernel(const VecArgsT<T> a) {
-  pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32];
   if (gated_out(a.red.S, a.red.gate)) return;
@@ -1126,13 +1167,13 @@ __global__ void __launch_bounds__(kVecThreads) bicg_restart_kernel(const VecArgs
       a.r[i] = r; a.r0[i] = r;
       v[0] = dacc(r, r, v[0]);
     });
+  pdl_launch_dependents();
   finish_reduction<1, kVecThreads>(a.red, v, scratch, a.history);
 }
 
 // BiCGSTAB :82-85: beta = (rho/rho_old)(alpha/w); p = r + beta (p - w v); y = D^-1 p
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) bicg_p_kernel(const VecArgsT<T> a) {
-  pdl_launch_dependents();
   pdl_wait();
   if (gated_out(a.red.S, a.red.gate)) return;
   const Scalars* S = a.red.S;
@@ -1160,7 +1201,6 @@ __global__ void __launch_bounds__(kVecThreads) bicg_p_kernel(const VecArgsT<T> a
 // BiCGSTAB :90-92: s = r - alpha v; z = D^-1 s
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) bicg_s_kernel(const VecArgsT<T> a) {
-  pdl_launch_dependents();
   pdl_wait();
   if (gated_out(a.red.S, a.red.gate)) return;
   const T alpha = static_cast<T>(a.red.S->alpha);
@@ -1185,7 +1225,6 @@ __global__ void __launch_bounds__(kVecThreads) bicg_s_kernel(const VecArgsT<T> a
 // BiCGSTAB :100-101 and the next loop head :67,:71: x += alpha y + w z; r = s - w t; ||r||^2; r0.r
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) bicg_update_kernel(const VecArgsT<T> a) {
-  pdl_launch_dependents();
   pdl_wait();
   __shared__ double scratch[32 * 2];
   if (gated_out(a.red.S, a.red.gate)) return;
@@ -1210,6 +1249,7 @@ __global__ void __launch_bounds__(kVecThreads) bicg_update_kernel(const VecArgsT
       elem(x, a.y[i], a.z[i], a.s[i], a.t[i], a.r0[i], r);
       a.x[i] = x; a.r[i] = r;
     });
+  pdl_launch_dependents();
   finish_reduction<2, kVecThreads>(a.red, v, scratch, a.history);
 }
 
@@ -1217,7 +1257,6 @@ __global__ void __launch_bounds__(kVecThreads) bicg_update_kernel(const VecArgsT
 // with at least the iterations left that the reference needs to spread it over x (see kEpiCgInit); otherwise nothing.
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) finalize_kernel(const VecArgsT<T> a) {
-  pdl_launch_dependents();
   pdl_wait();
   const bool zero = a.red.S->rhs_zero != 0, nan = a.red.S->numerical_issue == 2;
   if (!zero && !nan) return;
@@ -1348,7 +1387,7 @@ __global__ void __launch_bounds__(kSpmvThreads, 1024 / kSpmvThreads) cg_persiste
   // S changes only inside barrier epilogues, so after every barrier all CTAs read the same control state
   while (!__ldcg(&S->stop)) {
     if (!first) {
-      cg_direction_body<T>(a.ve, static_cast<T>(__ldcg(&S->alpha)), static_cast<T>(__ldcg(&S->beta)), true);
+      cg_direction_body<T>(a.ve, static_cast<T>(__ldcg(&S->alpha)), static_cast<T>(__ldcg(&S->beta)), kDirBoth);
       grid_sync<0, kSpmvThreads>(red_none, nullptr, red_scratch, a.ve.history, a.bar_count, a.bar_gen, gen);
     }
     first = false;
@@ -1367,7 +1406,7 @@ __global__ void __launch_bounds__(kSpmvThreads, 1024 / kSpmvThreads) cg_persiste
     }
   }
   if (!first) {  // the last iteration's x += alpha p is still owed (the loop stopped before its direction pass)
-    cg_direction_body<T>(a.ve, static_cast<T>(__ldcg(&S->alpha)), T(0), false);
+    cg_direction_body<T>(a.ve, static_cast<T>(__ldcg(&S->alpha)), T(0), kDirXOnly);
     if (blockIdx.x == 0 && threadIdx.x == 0) S->n_xapplied = S->n_update;
   }
   if (pending) {  // tiles prefetched for a product that will not happen: wait until the copies have landed

@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmm_staged_kernel(const SpmmArg
   SpmvCta<double> cx;
   spmv_cta_init(a.sp, cx, smem, full_bar, long_scratch);
   spmv_prefetch(a.sp, cx);
+  pdl_wait();
   if (multi_gated_out(a.m.S, a.m.gate)) {  // let the copies land, then leave
     for (int k = 0; k < a.sp.stages; ++k)
       if (static_cast<int>(blockIdx.x + k * gridDim.x) < a.sp.ntiles) mbar_wait(&full_bar[k], 0);
@@ -228,12 +229,17 @@ __global__ void __launch_bounds__(kSpmvThreads) spmm_staged_kernel(const SpmmArg
 #pragma unroll
   for (int q = 0; q < K; ++q) d0[q] = 0.0;
   const int S = a.sp.stages, G = gridDim.x, tid = threadIdx.x;
+  Tile tl_next = (static_cast<int>(blockIdx.x) < a.sp.ntiles) ? a.sp.tiles[blockIdx.x] : Tile{};
   for (int k = 0;; ++k) {
     const int t = blockIdx.x + k * G;
     if (t >= a.sp.ntiles) break;
     const int s = k % S;
     const unsigned parity = (k / S) & 1;
-    const Tile tl = a.sp.tiles[t];
+    const Tile tl = tl_next;  // descriptors one round ahead, as in spmv_tiles
+    if (t + G < a.sp.ntiles) tl_next = a.sp.tiles[t + G];
+    const bool refill = (tid == 0) && (t + S * G < a.sp.ntiles);
+    Tile tl_refill = tl;
+    if (refill) tl_refill = a.sp.tiles[t + S * G];
     const int nrows = tl.meta & 0xFFFF;
     const int lg = (tl.meta >> 16) & 0xFF;
     mbar_wait(&full_bar[s], parity);
@@ -251,10 +257,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmm_staged_kernel(const SpmmArg
       default: tile_rows_reduce_k<K, 5>(sv, sc, srp, nrows, tl.row0, vb0, cb0, a.x, a.y, a.x, d0); break;
     }
     __syncthreads();
-    if (tid == 0) {
-      const int t2 = t + S * G;
-      if (t2 < a.sp.ntiles) spmv_issue(a.sp, cx, t2, s);
-    }
+    if (refill) spmv_issue_tile<double>(a.sp, cx, tl_refill, s);
   }
   if (a.ndot) finish_reduction_multi<1, K, kSpmvThreads>(a.m, d0, red_scratch);
 }
@@ -282,6 +285,7 @@ __device__ __forceinline__ void vec_loop_rows(long long n, FR fr) {
 // ConjugateGradient.h:43-67 for K columns
 template <int K>
 __global__ void __launch_bounds__(kVecThreads) cg_init_multi_kernel(const MultiArgs<K> a) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (B200S_PDL=1)
   __shared__ double scratch[32 * 3 * K];
   const bool guess = a.S[0].use_guess != 0;
   double v[3 * K];
@@ -315,6 +319,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_init_multi_kernel(const MultiA
 // ConjugateGradient.h:75-84 for K columns (x update deferred as in cg_update_body)
 template <int K>
 __global__ void __launch_bounds__(kVecThreads) cg_update_multi_kernel(const MultiArgs<K> a) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (B200S_PDL=1)
   __shared__ double scratch[32 * 2 * K];
   if (multi_gated_out(a.S, a.gate)) return;
   double alpha[K];
@@ -345,6 +350,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_multi_kernel(const Mult
 // that column has just stopped, p = D^-1 r + beta p.
 template <int K>
 __global__ void __launch_bounds__(kVecThreads) cg_direction_multi_kernel(const MultiArgs<K> a, unsigned int* ticket) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (B200S_PDL=1)
   double alpha[K], beta[K];
   bool pend[K], upd[K];
   bool any = false;
@@ -384,6 +390,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_direction_multi_kernel(const M
 // x = 0 for columns with ||b|| == 0, x = NaN for columns that ran into a non-finite residual (see finalize_kernel)
 template <int K>
 __global__ void __launch_bounds__(kVecThreads) finalize_multi_kernel(const MultiArgs<K> a) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (B200S_PDL=1)
   bool zero[K], nan[K], any = false;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
