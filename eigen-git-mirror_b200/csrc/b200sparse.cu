@@ -1050,10 +1050,11 @@ int configure_spmv(b200s_handle* h) {
   if (stage * stages > 220 * 1024) return fail(h, B200S_ERR_INVALID, "tile_nnz/tile_rows too large for shared memory");
   h->spmv_stages = stages;
   h->spmv_smem = static_cast<int>(stage * stages);
-  // float tiles hold two thirds of the bytes of double tiles: one more stage gives the same bytes in flight per CTA
-  // in the same shared memory (a float tile drains in 2/3 of the time, so two stages do not cover the refill latency)
+  // float tiles hold two thirds of the bytes of double tiles.  A third stage (same bytes in flight per CTA as double)
+  // was measured and rejected: it costs two of the six resident CTAs per SM and the 7-point product drops from 0.816 to
+  // 0.750 of the HBM figure (profiles/r2_exp_l2_persist_f32_stages.txt) -- resident warps matter more than depth.
   const size_t stage32 = spmv_stage_bytes<float>(p.tile_nnz, p.tile_rows_cap);
-  int stages32 = std::max(2, std::min(8, env_int("B200S_SPMV_STAGES_F32", stages + 1)));
+  int stages32 = std::max(2, std::min(8, env_int("B200S_SPMV_STAGES_F32", stages)));
   while (stages32 > 2 && stage32 * stages32 > std::max(budget, stage * stages)) --stages32;
   h->spmv_stages_f32 = stages32;
   h->spmv_smem_f32 = static_cast<int>(stage32 * stages32);

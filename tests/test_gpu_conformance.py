@@ -20,3 +20,16 @@ def test_reference_driver_on_b200_solvers(seed, egm):
         pytest.skip(f"{exe} not built (needs /root/reference: make -C oracle conformance)")
     res = subprocess.run([exe, f"s{seed}", "r3"], capture_output=True, text=True, timeout=800)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_row_partitioned_path_from_cpp(world, egm):
+    """oracle/_ref/distributed_b200: one forked process per GPU, b200::ConjugateGradient / BiCGSTAB / SparseOperator with
+    setDistributed() and a shared-memory all-gather in place of MPI, against the reference's CPU solvers."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "distributed_b200")
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs /root/reference: make -C oracle distributed)")
+    if egm.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    res = subprocess.run([exe, str(world), "24"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and f"all {world} ranks ok" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

@@ -46,7 +46,7 @@ def main():
             continue
         if cur is None or "/*" not in line:
             continue
-        ins = re.search(r"/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+        ins = re.search(r"/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
         if not ins:
             continue
         total += 1
