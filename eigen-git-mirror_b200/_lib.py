@@ -93,6 +93,9 @@ def lib() -> C.CDLL:
     L.b200s_plan_probe.restype = i64
     L.b200s_plan_probe_csr.argtypes = [i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64]
     L.b200s_plan_probe_csr.restype = i64
+    L.b200s_plan_probe_selfadjoint.argtypes = [C.POINTER(Config), i64, i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, vp,
+                                               vp, i64]
+    L.b200s_plan_probe_selfadjoint.restype = i64
     L.b200s_plan_probe_span.argtypes = [i64, i64, vp, vp, vp, C.c_int]
     L.b200s_plan_probe_span.restype = i64
     _lib = L

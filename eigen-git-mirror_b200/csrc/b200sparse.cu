@@ -881,12 +881,23 @@ int solve_multi_device(b200s_handle* h, int64_t ncols, const double* B, int64_t 
 template <typename T>
 int factorize_impl(b200s_handle* h, const T* values, int precond) {
   if (!h->analyzed) return fail(h, B200S_ERR_INVALID, "factorize: call analyze_pattern first (IterativeSolverBase.h:218 asserts m_analysisIsOk)");
-  if (!values && h->plan.input_nnz > 0) return fail(h, B200S_ERR_INVALID, "factorize: values is null");
+  const Plan& p = h->plan;
+  int rc;
+  // Row-partitioned one-triangle input: the mirror images of entries stored on other ranks arrive through the
+  // config's allgather (setup path, host memory).  A collective: entered before any early return that depends on
+  // this rank's arguments alone, so that a bad argument on one rank cannot leave the others waiting.
+  std::vector<unsigned char> imports;
+  if (!p.tri_counts.empty()) {
+    std::vector<unsigned char> zeros;
+    const void* src_vals = values;
+    if (!values) { zeros.assign(static_cast<size_t>(std::max<int64_t>(p.input_nnz, 1)) * sizeof(T), 0); src_vals = zeros.data(); }
+    std::string err;
+    if ((rc = exchange_mirror_values(h->cfg, p, src_vals, sizeof(T), imports, err))) return fail(h, rc, err);
+  }
+  if (!values && p.input_nnz > 0) return fail(h, B200S_ERR_INVALID, "factorize: values is null");
   if (precond != B200S_PRECOND_IDENTITY && precond != B200S_PRECOND_JACOBI)
     return fail(h, B200S_ERR_INVALID, "factorize: precond must be 0 (identity) or 1 (Jacobi)");
   CK(cudaSetDevice(h->device));
-  const Plan& p = h->plan;
-  int rc;
   if ((rc = dev_alloc(h, h->vals, static_cast<size_t>(p.nnz) * sizeof(T) + 64))) return rc;
   if (h->scalar_bytes != static_cast<int>(sizeof(T))) {  // graphs bake pointers/types: rebuild lazily
     destroy_graphs(h->cg);
@@ -901,8 +912,10 @@ int factorize_impl(b200s_handle* h, const T* values, int precond) {
     if (p.nnz) CK(cudaMemcpyAsync(h->vals.p, values, static_cast<size_t>(p.nnz) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   } else {
     DevBuf staging;
-    if ((rc = dev_alloc(h, staging, static_cast<size_t>(p.input_nnz) * sizeof(T) + 64))) return rc;
+    if ((rc = dev_alloc(h, staging, static_cast<size_t>(p.input_nnz + p.n_import) * sizeof(T) + 64))) return rc;
     if (p.input_nnz) CK(cudaMemcpyAsync(staging.p, values, static_cast<size_t>(p.input_nnz) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    if (!imports.empty())  // mirrors stored on other ranks sit behind the caller's own values (plan.h: src >= input_nnz)
+      CK(cudaMemcpyAsync(staging.as<T>() + p.input_nnz, imports.data(), imports.size(), cudaMemcpyHostToDevice, h->stream));
     if (p.nnz) {
       gather_values_kernel<T><<<h->sm_count * 4, 256, 0, h->stream>>>(p.nnz, h->src.as<int32_t>(), staging.as<T>(), h->vals.as<T>());
       CK(cudaGetLastError());
@@ -1603,6 +1616,38 @@ int64_t b200s_plan_probe_csr(int64_t rows, int64_t nnz, const int32_t* rowptr, c
   if (out_colidx && n > 0) std::memcpy(out_colidx, p.colidx_ptr(), sizeof(int32_t) * static_cast<size_t>(n));
   if (out_src)
     for (int64_t k = 0; k < n; ++k) out_src[k] = p.src.empty() ? static_cast<int32_t>(k) : p.src[k];
+  return p.nnz;
+}
+
+int64_t b200s_plan_probe_selfadjoint(const b200s_config* cfg, int64_t rows, int64_t cols, int64_t nnz,
+                                     const int32_t* rowptr, const int32_t* colidx, const int32_t* inner_nnz, int uplo,
+                                     const int64_t* row_starts, const double* values, int32_t* out_rowptr,
+                                     int64_t* out_cols, double* out_values, int64_t cap) {
+  b200s_config c;
+  std::memset(&c, 0, sizeof(c));
+  c.world = 1;
+  if (cfg) std::memcpy(&c, cfg, std::min<size_t>(sizeof(c), cfg->struct_size > 0 ? cfg->struct_size : sizeof(c)));
+  if (c.world <= 0) c.world = 1;
+  Plan p;
+  std::string err;
+  int rc = build_plan(c, rows, cols, nnz, rowptr, colidx, inner_nnz, uplo, row_starts, p, err);
+  std::vector<unsigned char> imports;
+  if (!rc && values) rc = exchange_mirror_values(c, p, values, sizeof(double), imports, err);
+  if (rc) {
+    g_create_error = err;
+    return rc;
+  }
+  if (out_rowptr) std::memcpy(out_rowptr, p.rowptr.data(), sizeof(int32_t) * static_cast<size_t>(rows + 1));
+  const int64_t n = std::min<int64_t>(cap, p.nnz);
+  const int32_t* lc = p.colidx_ptr();
+  const double* imp = reinterpret_cast<const double*>(imports.data());
+  for (int64_t k = 0; k < n; ++k) {
+    if (out_cols) out_cols[k] = (p.world == 1 || lc[k] < p.rows) ? p.row0 + lc[k] : p.ghost_cols[lc[k] - p.rows];
+    if (out_values && values) {
+      const int64_t s = p.src.empty() ? k : p.src[k];
+      out_values[k] = s < p.input_nnz ? values[s] : imp[s - p.input_nnz];
+    }
+  }
   return p.nnz;
 }
 

@@ -112,6 +112,104 @@ int canonicalise(int64_t rows, int64_t nnz, const int32_t* rowptr, const int32_t
   return 0;
 }
 
+// One stored triangle of a ROW-PARTITIONED symmetric matrix -> this rank's rows of the full matrix (global columns).
+// The reference has no counterpart (it is single-process); the single-rank case is `canonicalise` above, and the
+// operator is the one SparseSelfAdjointView defines (SparseSelfAdjointView.h:279-337): stored triangle + its mirror.
+int canonicalise_distributed(const b200s_config& cfg, int64_t rows, const int32_t* rowptr, const int32_t* colidx,
+                             const int32_t* inner_nnz, int uplo, Plan& p, std::string& err) {
+  auto row_end = [&](int64_t i) { return inner_nnz ? rowptr[i] + inner_nnz[i] : rowptr[i + 1]; };
+  const bool lower = (uplo == B200S_LOWER);
+  const int W = p.world;
+  const int64_t lo = p.row0, hi = p.row0 + rows;
+  auto owner = [&](int64_t c) {
+    int q = static_cast<int>(std::upper_bound(p.row_starts.begin(), p.row_starts.end(), c) - p.row_starts.begin()) - 1;
+    return std::max(0, std::min(W - 1, q));
+  };
+  struct Ent { int64_t col; int64_t src; };
+  std::vector<std::vector<Ent>> row_ents(rows);
+  struct Exp { int64_t row, col; int32_t src; };
+  std::vector<std::vector<Exp>> exports(W);
+  int64_t span = 0;
+  for (int64_t il = 0; il < rows; ++il) {
+    const int64_t i = lo + il;
+    span = std::max<int64_t>(span, row_end(il));
+    for (int32_t k = rowptr[il]; k < row_end(il); ++k) {
+      const int64_t c = colidx[k];
+      if (c < 0 || c >= p.cols) { err = "column index out of range"; return B200S_ERR_INVALID; }
+      if (c == i) { row_ents[il].push_back({c, k}); continue; }
+      if (!(lower ? (c < i) : (c > i))) continue;  // the other triangle is ignored, as selfadjointView does
+      row_ents[il].push_back({c, k});              // the stored entry (i, c)
+      if (c >= lo && c < hi) row_ents[c - lo].push_back({i, k});   // its mirror (c, i) lives here too
+      else exports[owner(c)].push_back({c, i, k});                  // ... or on the rank that owns row c
+    }
+  }
+  p.input_nnz = span;
+  // ---- who exports how much to whom ----
+  std::vector<int64_t> mine(W, 0);
+  for (int d = 0; d < W; ++d) mine[d] = static_cast<int64_t>(exports[d].size());
+  p.tri_counts.assign(static_cast<size_t>(W) * W, 0);
+  if (cfg.allgather(cfg.allgather_ctx, mine.data(), p.tri_counts.data(), sizeof(int64_t) * W)) {
+    err = "allgather(mirror counts) failed"; return B200S_ERR_COMM;
+  }
+  int64_t max_total = 1;
+  for (int q = 0; q < W; ++q) {
+    int64_t t = 0;
+    for (int d = 0; d < W; ++d) t += p.tri_counts[static_cast<size_t>(q) * W + d];
+    max_total = std::max(max_total, t);
+  }
+  // ---- the (row, col) of every exported mirror, grouped by destination ----
+  std::vector<int64_t> send(static_cast<size_t>(max_total) * 2, -1), recv(static_cast<size_t>(max_total) * 2 * W);
+  p.export_src.clear();
+  {
+    size_t o = 0;
+    for (int d = 0; d < W; ++d)
+      for (const Exp& e : exports[d]) {
+        send[2 * o] = e.row;
+        send[2 * o + 1] = e.col;
+        p.export_src.push_back(e.src);
+        ++o;
+      }
+  }
+  if (cfg.allgather(cfg.allgather_ctx, send.data(), recv.data(), sizeof(int64_t) * send.size())) {
+    err = "allgather(mirror entries) failed"; return B200S_ERR_COMM;
+  }
+  p.n_import = 0;
+  for (int q = 0; q < W; ++q) {
+    int64_t off = 0;
+    for (int d = 0; d < p.rank; ++d) off += p.tri_counts[static_cast<size_t>(q) * W + d];
+    const int64_t cnt = p.tri_counts[static_cast<size_t>(q) * W + p.rank];
+    const int64_t* lst = recv.data() + static_cast<size_t>(q) * max_total * 2;
+    for (int64_t j = 0; j < cnt; ++j) {
+      const int64_t r = lst[2 * (off + j)], c = lst[2 * (off + j) + 1];
+      if (r < lo || r >= hi || c < 0 || c >= p.cols) { err = "mirror exchange inconsistent across ranks"; return B200S_ERR_COMM; }
+      row_ents[r - lo].push_back({c, span + p.n_import});
+      ++p.n_import;
+    }
+  }
+  // ---- assemble: rows sorted by column (stable, so a sorted input stays sorted) ----
+  int64_t total = 0;
+  for (int64_t il = 0; il < rows; ++il) total += static_cast<int64_t>(row_ents[il].size());
+  if (total >= (int64_t(1) << 31) - 64 || span + p.n_import >= (int64_t(1) << 31) - 64) {
+    err = "expanded nnz does not fit int32"; return B200S_ERR_UNSUPPORTED;
+  }
+  p.rowptr.assign(rows + 1, 0);
+  p.colidx.resize(total);
+  p.src.resize(total);
+  int64_t o = 0;
+  for (int64_t il = 0; il < rows; ++il) {
+    p.rowptr[il] = static_cast<int32_t>(o);
+    auto& v = row_ents[il];
+    std::stable_sort(v.begin(), v.end(), [](const Ent& a, const Ent& b) { return a.col < b.col; });
+    for (const Ent& e : v) {
+      p.colidx[o] = static_cast<int32_t>(e.col);
+      p.src[o] = static_cast<int32_t>(e.src);
+      ++o;
+    }
+  }
+  p.rowptr[rows] = static_cast<int32_t>(o);
+  return 0;
+}
+
 }  // namespace
 
 static void build_tiles(Plan& p, const std::vector<uint8_t>& row_is_boundary) {
@@ -210,7 +308,6 @@ int build_plan(const b200s_config& cfg, int64_t rows, int64_t cols, int64_t nnz,
   } else {
     if (!row_starts) { err = "row_starts is required when world > 1"; return B200S_ERR_INVALID; }
     if (!cfg.allgather) { err = "config.allgather is required when world > 1"; return B200S_ERR_COMM; }
-    if (uplo != B200S_BOTH) { err = "Lower/Upper storage is only supported on one GPU"; return B200S_ERR_UNSUPPORTED; }
     p.row_starts.assign(row_starts, row_starts + p.world + 1);
     if (p.row_starts[0] != 0 || p.row_starts[p.world] != cols) { err = "row_starts must span [0, cols]"; return B200S_ERR_INVALID; }
     for (int q = 0; q < p.world; ++q)
@@ -219,7 +316,9 @@ int build_plan(const b200s_config& cfg, int64_t rows, int64_t cols, int64_t nnz,
   }
   p.row0 = p.row_starts[p.rank];
 
-  int rc = canonicalise(rows, nnz, rowptr, colidx, inner_nnz, uplo, p, err);
+  int rc = (p.world > 1 && uplo != B200S_BOTH)
+               ? canonicalise_distributed(cfg, rows, rowptr, colidx, inner_nnz, uplo, p, err)
+               : canonicalise(rows, nnz, rowptr, colidx, inner_nnz, uplo, p, err);
   if (rc) return rc;
   p.nnz = p.rowptr[rows];
   const bool own_cols = !p.colidx.empty() || p.nnz == 0;
@@ -320,6 +419,39 @@ int build_plan(const b200s_config& cfg, int64_t rows, int64_t cols, int64_t nnz,
     p.tiles.clear();
     build_tiles(p, row_is_boundary);
   }
+  return 0;
+}
+
+int exchange_mirror_values(const b200s_config& cfg, const Plan& p, const void* values, size_t elem,
+                           std::vector<unsigned char>& imports, std::string& err) {
+  imports.clear();
+  if (p.tri_counts.empty()) return 0;
+  const int W = p.world;
+  int64_t max_total = 1;
+  for (int q = 0; q < W; ++q) {
+    int64_t t = 0;
+    for (int d = 0; d < W; ++d) t += p.tri_counts[static_cast<size_t>(q) * W + d];
+    max_total = std::max(max_total, t);
+  }
+  // my exported values in export order (grouped by destination), padded to the longest list of any rank
+  std::vector<unsigned char> send(static_cast<size_t>(max_total) * elem, 0), recv(send.size() * W);
+  const unsigned char* v = static_cast<const unsigned char*>(values);
+  for (size_t o = 0; o < p.export_src.size(); ++o)
+    std::memcpy(send.data() + o * elem, v + static_cast<size_t>(p.export_src[o]) * elem, elem);
+  if (!cfg.allgather || cfg.allgather(cfg.allgather_ctx, send.data(), recv.data(), send.size())) {
+    err = "allgather(mirror values) failed";
+    return B200S_ERR_COMM;
+  }
+  imports.resize(static_cast<size_t>(p.n_import) * elem);
+  size_t o = 0;
+  for (int q = 0; q < W; ++q) {  // same order as canonicalise_distributed numbered the imports
+    int64_t off = 0;
+    for (int d = 0; d < p.rank; ++d) off += p.tri_counts[static_cast<size_t>(q) * W + d];
+    const int64_t cnt = p.tri_counts[static_cast<size_t>(q) * W + p.rank];
+    if (cnt) std::memcpy(imports.data() + o, recv.data() + (static_cast<size_t>(q) * max_total + off) * elem, static_cast<size_t>(cnt) * elem);
+    o += static_cast<size_t>(cnt) * elem;
+  }
+  if (o != imports.size()) { err = "mirror value exchange inconsistent with the plan"; return B200S_ERR_COMM; }
   return 0;
 }
 

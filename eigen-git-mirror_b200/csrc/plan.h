@@ -47,6 +47,14 @@ struct Plan {
   // src[k] = index into the caller's value array of local entry k; empty = identity.
   std::vector<int32_t> src;
   int64_t input_nnz = 0;  // slots of the caller's value array that are read: one past the last referenced slot
+  // One stored triangle on a row-partitioned matrix (uplo != BOTH, world > 1): the mirror image (c, i) of a stored entry
+  // (i, c) belongs to the rank that owns row c.  export_src lists, grouped by destination rank, the value slots whose
+  // mirrors other ranks need; tri_counts[q*world + d] = how many rank q exports to rank d (known to every rank);
+  // the n_import values this rank receives (source rank ascending, then the source's export order) are staged behind
+  // the caller's input_nnz values, and `src` refers to them as input_nnz + j.  factorize() exchanges the values.
+  std::vector<int32_t> export_src;
+  std::vector<int64_t> tri_counts;
+  int64_t n_import = 0;
   // Halo plan.
   std::vector<int64_t> ghost_cols;     // sorted global ids; local column of ghost g is rows + g
   std::vector<int64_t> recv_counts;    // [world] ghosts owned by each peer
@@ -68,6 +76,13 @@ struct Plan {
 int build_plan(const b200s_config& cfg, int64_t rows, int64_t cols, int64_t nnz, const int32_t* rowptr,
                const int32_t* colidx, const int32_t* inner_nnz, int uplo, const int64_t* row_starts, Plan& plan,
                std::string& err);
+
+// Row-partitioned one-triangle input (plan.tri_counts non-empty): collects, through the config's allgather, the values
+// of the mirror entries other ranks store for this rank's rows.  `values` is the caller's array (elements of `elem`
+// bytes); `imports` receives plan.n_import elements, to be staged right behind the caller's plan.input_nnz values.
+// Every rank must call it (it is a collective).  Returns 0 or a negative b200s_status.
+int exchange_mirror_values(const b200s_config& cfg, const Plan& plan, const void* values, size_t elem,
+                           std::vector<unsigned char>& imports, std::string& err);
 
 void fill_tile_stats(const Plan& plan, b200s_stats* st);
 

@@ -73,3 +73,34 @@ def canonical_csr(A, uplo: int = 3, inner_nnz=None):
     if n < 0:
         raise _lib.B200Error(int(n), L.b200s_last_error(None).decode())
     return rowptr, colidx[:n].copy(), src[:n].copy()
+
+
+def selfadjoint_rows(A, uplo: int, comm: Optional[Communicator] = None, inner_nnz=None):
+    """This rank's rows of the full self-adjoint matrix the device holds when ``A`` (this rank's row block, global
+    columns) stores one triangle: returns (rowptr, global column ids, values).  With a communicator the mirror images
+    stored by other ranks are fetched through its allgather -- a collective, every rank calls it (GPU-free)."""
+    A = _as_csr(A)
+    L = _lib.lib()
+    cfg = Config()
+    cfg.struct_size = C.sizeof(Config)
+    cfg.world = comm.world if comm else 1
+    cfg.rank = comm.rank if comm else 0
+    if comm:
+        cfg.allgather = comm.callback
+    inz = None if inner_nnz is None else np.ascontiguousarray(inner_nnz, np.int32)
+    rs = comm.row_starts if comm else None
+    nnz_in = int(A.colidx.shape[0])
+    vals = np.ascontiguousarray(A.vals, np.float64)
+    rowptr = np.zeros(A.rows + 1, np.int32)
+    args = (C.byref(cfg), A.rows, A.cols, nnz_in, _ptr(A.rowptr), _ptr(A.colidx), _ptr(inz), uplo, _ptr(rs), _ptr(vals),
+            _ptr(rowptr))
+    # the mirrors arriving from other ranks are not bounded by the local input: ask for the size first
+    n = L.b200s_plan_probe_selfadjoint(*args, None, None, 0)
+    if n < 0:
+        raise _lib.B200Error(int(n), L.b200s_last_error(None).decode())
+    cols = np.zeros(max(1, n), np.int64)
+    out = np.zeros(max(1, n), np.float64)
+    n = L.b200s_plan_probe_selfadjoint(*args, _ptr(cols), _ptr(out), int(n))
+    if n < 0:
+        raise _lib.B200Error(int(n), L.b200s_last_error(None).decode())
+    return rowptr, cols[:n].copy(), out[:n].copy()

@@ -122,7 +122,9 @@ const char* b200s_last_error(const b200s_handle* h /* NULL: error of the last fa
  *               entries [rowptr[i], rowptr[i]+inner_nnz[i]).
  *   uplo      : which stored triangle(s) define the operator.  LOWER / UPPER read one triangle and imply its mirror
  *               image, as ConjugateGradient<_,Lower> does through selfadjointView (ConjugateGradient.h:202-213); the
- *               device matrix is then the expanded full CSR.  Only world == 1 supports LOWER / UPPER.
+ *               device matrix is then the expanded full CSR.  With world > 1 the mirror image of an entry (i, c) belongs to
+ *               the rank that owns row c: analyze_pattern exchanges those patterns and factorize their values through
+ *               the config's allgather (setup only), so every rank passes just the triangle of its own rows.
  * It builds the partition / halo plan, the SpMV tiles with their per-tile row-binning, and uploads the pattern.
  * factorize uploads the values (same order as the pattern given to analyze_pattern) and builds the
  * preconditioner: invdiag[j] = 1/A_jj if stored and non-zero else 1 (BasicPreconditioners.h:64-79). */
@@ -246,6 +248,17 @@ int64_t b200s_plan_probe(const b200s_config* cfg, int64_t rows, int64_t cols, in
 int64_t b200s_plan_probe_csr(int64_t rows, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
                              const int32_t* inner_nnz, int uplo, int32_t* out_rowptr, int32_t* out_colidx,
                              int32_t* out_src, int64_t cap);
+
+/* GPU-free view of THIS RANK's rows of the device matrix analyze_pattern + factorize_f64 build from a row-partitioned
+ * input, in particular from one stored triangle (uplo LOWER / UPPER with world > 1: the mirror image of an entry stored
+ * by another rank is fetched through the config's allgather, pattern and values alike).  A collective when world > 1:
+ * every rank calls it.  out_rowptr has rows+1 entries; out_cols (GLOBAL column ids) and out_values (optional, needs
+ * `values`) receive up to `cap` entries in the order the SpMV kernel sums them.  Returns the number of local entries
+ * or a negative status. */
+int64_t b200s_plan_probe_selfadjoint(const b200s_config* cfg, int64_t rows, int64_t cols, int64_t nnz,
+                                     const int32_t* rowptr, const int32_t* colidx, const int32_t* inner_nnz, int uplo,
+                                     const int64_t* row_starts, const double* values, int32_t* out_rowptr,
+                                     int64_t* out_cols, double* out_values, int64_t cap);
 
 /* Number of leading slots of the caller's value array that factorize will read for this pattern (one past the last
  * slot any row references), or a negative status.  GPU-free. */

@@ -6,7 +6,10 @@ SpMV -- i.e. partition + ghost numbering + send lists are exactly what a correct
 
 mode "gpu" (one process per GPU): SpMV, CG and BiCGSTAB through the C ABI on the partitioned problem (a few dozen SpMV
 tiles per rank, interior and boundary); every rank gathers the pieces and compares with the oracle run on the whole
-problem.
+problem.  CG is repeated with one stored triangle per rank (UpLo = Lower, Upper) and must give identical bits.
+
+mode "tri" (CPU, gloo): the row-partitioned self-adjoint expansion (pattern + values of the mirrors exchanged through
+the allgather callback) equals the rows of the full symmetric matrix, entry for entry.
 
 mode "fullsize" (one process per GPU): BASELINE.json's configurations at full size -- name is cg_256, bicg_256 or
 cg_512 -- row-partitioned over the visible GPUs and compared with the reference fixtures of
@@ -76,7 +79,7 @@ def main():
     dist.init_process_group(backend="gloo")
     if mode == "fullsize":
         return fullsize(name, rank, world, dist, egm, wl)
-    A, align = make(name, big=(mode != "plan"))
+    A, align = make(name, big=(mode not in ("plan", "tri")))
     # stencils: plane-aligned equal blocks; irregular rows: blocks balanced by the bytes an iteration streams
     starts = egm.partition_rows(A.rows, world, align=align, rowptr=(A.rowptr if name == "powerlaw" else None))
     r0, r1 = int(starts[rank]), int(starts[rank + 1])
@@ -113,6 +116,43 @@ def main():
             nb = (rank > 0) + (rank < world - 1)
             assert len(ext) == 144 * nb and v.stats["tiles_boundary"] <= 2 * nb + 1
         print(f"rank {rank}: plan ok, ghosts {len(ext)}, send {len(v.send_rows)}")
+    elif mode == "tri":
+        # One stored triangle, row-partitioned: every rank passes the Lower (Upper) part of ITS rows only; the plan must
+        # hand each rank exactly its rows of the full self-adjoint matrix (pattern, values and summation order), with
+        # the mirrors of entries stored by other ranks fetched through the allgather.
+        import scipy.sparse as sp
+        S = A.to_scipy()
+        S = ((S + S.T) * 0.5).tocsr()        # symmetric whatever the workload was
+        S.sort_indices()
+        for uplo, tri in ((egm.Lower, sp.tril), (egm.Upper, sp.triu)):
+            T = tri(S, format="csr")
+            T.sort_indices()
+            Tb = T[r0:r1]
+            blk = wl.CsrMatrix(r1 - r0, A.cols, Tb.indptr.astype(np.int32), Tb.indices.astype(np.int32),
+                               Tb.data.copy(), r0)
+            rp, cols, vals = planning.selfadjoint_rows(blk, uplo, comm)
+            want = S[r0:r1]
+            assert np.array_equal(rp, want.indptr), "row pointers of the expanded block"
+            assert np.array_equal(cols, want.indices), "columns (sorted input stays sorted)"
+            assert np.array_equal(vals, want.data), "values, own and imported"
+            # uncompressed storage with a stray entry of the other triangle (ignored, as selfadjointView does)
+            if uplo == egm.Lower and blk.rows:
+                pad = 2
+                rp_u = (blk.rowptr + pad * np.arange(blk.rows + 1)).astype(np.int32)
+                ci_u = np.zeros(int(rp_u[-1]), np.int32)
+                va_u = np.full(int(rp_u[-1]), 777.0)
+                inner = np.diff(blk.rowptr).astype(np.int32)
+                for i in range(blk.rows):
+                    n_i = inner[i]
+                    ci_u[rp_u[i]:rp_u[i] + n_i] = blk.colidx[blk.rowptr[i]:blk.rowptr[i + 1]]
+                    va_u[rp_u[i]:rp_u[i] + n_i] = blk.vals[blk.rowptr[i]:blk.rowptr[i + 1]]
+                if r0 + 1 < A.cols:      # entry (r0, cols-1) lies in the upper triangle: must be skipped
+                    ci_u[rp_u[0] + inner[0]] = A.cols - 1
+                    inner[0] += 1
+                unc = wl.CsrMatrix(blk.rows, A.cols, rp_u, ci_u, va_u, r0)
+                rp2, cols2, vals2 = planning.selfadjoint_rows(unc, uplo, comm, inner_nnz=inner)
+                assert np.array_equal(rp2, rp) and np.array_equal(cols2, cols) and np.array_equal(vals2, vals)
+        print(f"rank {rank}: tri ok, block nnz {len(cols)}")
     elif mode == "deadpeer":
         s = egm.ConjugateGradient(Ab, comm=comm)
         b = np.asarray(A.to_scipy() @ wl.random_vector(A.rows, 12345))
@@ -152,6 +192,21 @@ def main():
             xl3 = s.solveWithGuess(b[r0:r1], xl)
             assert s.iterations() == 0
             msg = f"cg iters {s.iterations()} rel {rel:.2e}"
+            # ConjugateGradient<_, Lower> / <_, Upper> row-partitioned: every rank passes one triangle of its rows; the
+            # device matrix is the same full block (same summation order for sorted rows) => identical bits
+            if name in ("poisson3d", "powerlaw"):
+                St = A.to_scipy()
+                for uplo, tri in ((egm.Lower, sp.tril), (egm.Upper, sp.triu)):
+                    Tb = tri(St, format="csr")[r0:r1]
+                    Tb.sort_indices()
+                    blk = wl.CsrMatrix(r1 - r0, A.cols, Tb.indptr.astype(np.int32), Tb.indices.astype(np.int32),
+                                       Tb.data.copy(), r0)
+                    st = egm.ConjugateGradient(blk, uplo=uplo, comm=comm)
+                    st.setTolerance(1e-10)
+                    xt = st.solve(b[r0:r1])
+                    assert st.iterations() == s.iterations() and np.array_equal(xt, xl), (uplo, st.iterations())
+                    st.close()
+                msg += "; Lower/Upper identical"
         else:
             msg = ""
         s2 = egm.BiCGSTAB(Ab, comm=comm)

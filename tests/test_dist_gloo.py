@@ -24,3 +24,13 @@ def test_partition_and_halo_plan(world, name):
     res = launch(world, "plan", name)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert res.stdout.count("plan ok") == world
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world,name", [(2, "poisson3d"), (3, "powerlaw"), (2, "varcoef3d")])
+def test_one_triangle_row_partitioned(world, name):
+    """ConjugateGradient<_, Lower> / <_, Upper> on a row-partitioned matrix: each rank stores one triangle of its rows,
+    the plan exchanges the mirror images (SparseSelfAdjointView.h:279-337 applied across ranks)."""
+    res = launch(world, "tri", name)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.stdout.count("tri ok") == world
