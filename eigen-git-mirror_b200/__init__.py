@@ -6,6 +6,7 @@ Layout
   solvers.py    host-side mirror of Eigen's solver interface over that C ABI (ctypes)
   planning.py   GPU-free view of the partition / halo / tile plan (host logic, testable on CPU)
   workloads.py  synthetic CSR matrices of BASELINE.json
+  preconditioners.py  IncompleteLUT / IncompleteCholesky: host factorization, GPU application (csrc/kernels_tri.cuh)
   marketio.py   MatrixMarket I/O with the reference's semantics (SparseExtra/MarketIO.h), host-side
   build.py      nvcc build (in-tree)
 
@@ -16,8 +17,9 @@ from . import solvers  # noqa: F401
 from .solvers import (GMRES, MINRES, BiCGSTAB, Communicator, ConjugateGradient, DiagonalPreconditioner,  # noqa: F401
                       IdentityPreconditioner, InvalidInput, LeastSquaresConjugateGradient, Lower, NoConvergence,
                       NumericalIssue, SparseOperator, Success, Upper, device_count, partition_rows)
+from .preconditioners import IncompleteCholesky, IncompleteLUT  # noqa: F401
 from ._lib import B200Error  # noqa: F401
 
 __all__ = ["ConjugateGradient", "BiCGSTAB", "LeastSquaresConjugateGradient", "MINRES", "GMRES", "SparseOperator", "Communicator", "partition_rows", "device_count",
            "Lower", "Upper", "Success", "NumericalIssue", "NoConvergence", "InvalidInput", "DiagonalPreconditioner",
-           "IdentityPreconditioner", "B200Error", "workloads"]
+           "IdentityPreconditioner", "IncompleteLUT", "IncompleteCholesky", "B200Error", "workloads"]

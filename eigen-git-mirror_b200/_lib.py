@@ -83,6 +83,26 @@ def lib() -> C.CDLL:
     L.b200s_lscg_solve_f64.argtypes = [H, H, vp, vp, C.c_int, dbl, i64, C.c_int, C.c_int] + out3
     L.b200s_minres_solve_f64.argtypes = [H, vp, vp, C.c_int, dbl, i64] + out3
     L.b200s_gmres_solve_f64.argtypes = [H, vp, vp, C.c_int, dbl, i64, i64] + out3
+    F = C.c_void_p
+    csr = [i64, vp, vp, vp]
+    L.b200s_ilut_f64.argtypes = csr + [dbl, C.c_int, vp, C.POINTER(F)]
+    L.b200s_ichol_f64.argtypes = csr + [C.c_int, dbl, vp, C.POINTER(F)]
+    L.b200s_factors_from_ilut_f64.argtypes = csr + [vp, C.POINTER(F)]
+    L.b200s_factors_from_ichol_f64.argtypes = csr + [vp, vp, C.POINTER(F)]
+    L.b200s_factors_destroy.argtypes = [F]
+    L.b200s_factors_destroy.restype = None
+    for name in ("info", "kind"):
+        getattr(L, f"b200s_factors_{name}").argtypes = [F]
+    for name in ("size", "nnz", "perm_size"):
+        getattr(L, f"b200s_factors_{name}").argtypes = [F]
+        getattr(L, f"b200s_factors_{name}").restype = i64
+    L.b200s_factors_get.argtypes = [F, vp, vp, vp, vp, vp]
+    L.b200s_factors_stage_sizes.argtypes = [F, C.c_int, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                                            C.POINTER(i32)]
+    L.b200s_factors_stage.argtypes = [F, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.b200s_factors_permscale.argtypes = [F, vp, vp, vp, vp, vp]
+    L.b200s_set_preconditioner.argtypes = [H, F]
+    L.b200s_precond_apply_f64.argtypes = [H, vp, vp]
     L.b200s_get_stats.argtypes = [H, C.POINTER(Stats)]
     L.b200s_get_invdiag_f64.argtypes = [H, vp]
     L.b200s_get_timeline.argtypes = [H, vp, C.c_int]

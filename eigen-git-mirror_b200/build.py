@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libb200sparse.so")
-SOURCES = ["b200sparse.cu", "plan.cpp"]
-HEADERS = ["kernels.cuh", "kernels_multi.cuh", "kernels_krylov.cuh", "krylov.inc", "device_state.h", "plan.h", os.path.join("..", "..", "include", "b200sparse.h")]
+SOURCES = ["b200sparse.cu", "plan.cpp", "factors.cpp"]
+HEADERS = ["kernels.cuh", "kernels_multi.cuh", "kernels_krylov.cuh", "krylov.inc", "precond.inc", "kernels_tri.cuh", "factors.h", "device_state.h", "plan.h", os.path.join("..", "..", "include", "b200sparse.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -20,6 +20,8 @@
 #include "kernels.cuh"
 #include "kernels_multi.cuh"
 #include "kernels_krylov.cuh"
+#include "kernels_tri.cuh"
+#include "factors.h"
 
 using namespace b200s;
 
@@ -45,7 +47,29 @@ struct GraphSet {
   const void* tag = nullptr;  // address the graph's kernels were built around (rebuilt when it moves)
 };
 
+// device copy of an incomplete factorization (csrc/factors.h): two level-scheduled triangular stages between
+// a gather/scale on the way in and one on the way out
+struct DevTriStage {
+  DevBuf rowptr, colidx, vals, diag, level_ptr, level_rows;
+  bool unit = true, fused = false;
+  int levels = 0;
+  std::vector<b200s::TriStage::Launch> launches;
+};
+struct DevFactors {
+  bool set = false;
+  int kind = 0;
+  int64_t n = 0;
+  DevTriStage st[2];
+  DevBuf pre_gather, post_gather, pre_scale, post_scale, x;
+  int64_t applies = 0;
+};
+
 }  // namespace
+
+// the opaque factors object of the C ABI is the host-side analysis result
+struct b200s_factors {
+  b200s::Factors f;
+};
 
 struct b200s_handle {
   b200s_config cfg{};
@@ -57,6 +81,8 @@ struct b200s_handle {
   bool analyzed = false, factorized = false;
   int scalar_bytes = 0;  // 8 = f64, 4 = f32
   int precond = B200S_PRECOND_JACOBI;
+  int precond_factorize = B200S_PRECOND_JACOBI;  // what factorize() built (set_preconditioner(NULL) returns to it)
+  DevFactors fac;
   int loop_mode = B200S_LOOP_WHILE_GRAPH;  // resolved per problem in analyze_pattern when AUTO was requested
   bool loop_auto = false;
   int spmv_impl = B200S_SPMV_STAGED;
@@ -108,6 +134,8 @@ int fail(b200s_handle* h, int code, const std::string& msg) {
   h->err = msg;
   return code;
 }
+
+void free_factors(b200s_handle* h);  // precond.inc
 
 int dev_alloc(b200s_handle* h, DevBuf& buf, size_t bytes, bool zero = false) {
   bytes = ((bytes + 255) & ~size_t(255)) + 256;  // slack: bulk copies read up to 16 B past the logical end
@@ -533,7 +561,7 @@ int build_graphs(b200s_handle* h, GraphSet& g, enqueue_fn init, enqueue_fn body,
 // The K-wide kernels cover row-lane tiles only; matrices with two-phase or long-row tiles (strongly irregular rows),
 // float factorizations and row-partitioned handles take the sequential per-column path, like the reference does.
 bool multi_supported(const b200s_handle* h) {
-  return h->factorized && h->scalar_bytes == 8 && h->plan.world == 1 && h->plan.n_stream == 0 && h->plan.n_long == 0 &&
+  return h->factorized && h->precond != B200S_PRECOND_FACTORS && h->scalar_bytes == 8 && h->plan.world == 1 && h->plan.n_stream == 0 && h->plan.n_long == 0 &&
          h->spmv_impl != B200S_SPMV_DIRECT && h->plan.rows == h->plan.cols && h->plan.rows > 0;
 }
 
@@ -837,6 +865,9 @@ int run_solve_multi(b200s_handle* h, int ncols, const double* B_dev, int64_t ldb
 
 // Any number of columns: batches of 8 / 4 / 2 through the K-wide kernels, a last single column (or everything, when
 // the handle does not support batching) through the single-column solver.  Column-major, device pointers.
+int cg_general_solve(b200s_handle* h, const double* b_src, double* x_dst, bool device_ptrs, int use_guess, double tol,
+                     int64_t max_iters, int64_t* iters_out, double* error_out, int* info_out);  // precond.inc
+
 int solve_multi_device(b200s_handle* h, int64_t ncols, const double* B, int64_t ldb, double* X, int64_t ldx,
                        int use_guess, double tol, int64_t max_iters, int64_t* iters_out, double* error_out,
                        int* info_out, int64_t* launches_out) {
@@ -864,7 +895,10 @@ int solve_multi_device(b200s_handle* h, int64_t ncols, const double* B, int64_t 
     } else {
       took = 1;
       const int64_t spmv_before = h->last_spmv;
-      rc = run_solve<double>(h, false, B + c * ldb, X + c * ldx, use_guess, tol, max_iters, it, er, in);
+      if (h->precond == B200S_PRECOND_FACTORS)
+        rc = cg_general_solve(h, B + c * ldb, X + c * ldx, true, use_guess, tol, max_iters, it, er, in);
+      else
+        rc = run_solve<double>(h, false, B + c * ldb, X + c * ldx, use_guess, tol, max_iters, it, er, in);
       h->last_spmv += spmv_before;
     }
     if (rc) return rc;
@@ -905,7 +939,8 @@ int factorize_impl(b200s_handle* h, const T* values, int precond) {
     for (GraphSet& g : h->cg_multi) destroy_graphs(g);
   }
   h->scalar_bytes = sizeof(T);
-  h->precond = precond;
+  h->precond = h->precond_factorize = precond;
+  free_factors(h);  // factors of the previous values are stale (IterativeSolverBase::factorize re-factorizes, :216-224)
   cudaEvent_t e0 = h->ev0, e1 = h->ev1;
   CK(cudaEventRecord(e0, h->stream));
   if (p.src.empty()) {
@@ -1194,7 +1229,9 @@ int configure_l2_persistence(b200s_handle* h) {
   return 0;
 }
 
+int k_precond(b200s_handle* h, int64_t n, const double* r, double* z);  // precond.inc
 #include "krylov.inc"
+#include "precond.inc"
 
 }  // namespace
 
@@ -1288,6 +1325,7 @@ void b200s_destroy(b200s_handle* h) {
   destroy_graphs(h->bicg);
   for (GraphSet& g : h->cg_multi) destroy_graphs(g);
   if (h->hSm) cudaFreeHost(h->hSm);
+  free_factors(h);
   for (int q = 0; q < static_cast<int>(h->peer_window.size()); ++q)
     if (q != h->plan.rank && h->peer_window[q]) cudaIpcCloseMemHandle(h->peer_window[q]);
   DevBuf* bufs[] = {&h->mx, &h->mr, &h->mp, &h->mq, &h->mb, &h->mS, &h->mpartials, &h->mstage,
@@ -1308,6 +1346,8 @@ int b200s_analyze_pattern(b200s_handle* h, int64_t rows, int64_t cols, int64_t n
   if (!h) return B200S_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   h->analyzed = h->factorized = false;
+  free_factors(h);
+  h->precond = h->precond_factorize;
   destroy_graphs(h->cg);
   destroy_graphs(h->bicg);
   for (GraphSet& g : h->cg_multi) destroy_graphs(g);
@@ -1418,15 +1458,125 @@ int b200s_spmv_device_f32(b200s_handle* h, const float* x, float* y, int reps, f
            double* error_out, int* info_out) {                                                                       \
     return IMPL<T>(h, BICG, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);                        \
   }
-B200S_SOLVE_ENTRY(b200s_cg_solve_f64, double, solve_host, false)
-B200S_SOLVE_ENTRY(b200s_bicgstab_solve_f64, double, solve_host, true)
+// double: an incomplete-factorization preconditioner (b200s_set_preconditioner) routes to the general loops of precond.inc
+#define B200S_SOLVE_ENTRY_F64(NAME, IMPL, BICG, DEVICE)                                                              \
+  int NAME(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,                \
+           int64_t* iters_out, double* error_out, int* info_out) {                                                   \
+    if (h && h->precond == B200S_PRECOND_FACTORS)                                                                    \
+      return (BICG ? bicgstab_general_solve : cg_general_solve)(h, b, x, DEVICE, use_guess, tol, max_iters,          \
+                                                                iters_out, error_out, info_out);                    \
+    return IMPL<double>(h, BICG, b, x, use_guess, tol, max_iters, iters_out, error_out, info_out);                   \
+  }
+B200S_SOLVE_ENTRY_F64(b200s_cg_solve_f64, solve_host, false, false)
+B200S_SOLVE_ENTRY_F64(b200s_bicgstab_solve_f64, solve_host, true, false)
 B200S_SOLVE_ENTRY(b200s_cg_solve_f32, float, solve_host, false)
 B200S_SOLVE_ENTRY(b200s_bicgstab_solve_f32, float, solve_host, true)
-B200S_SOLVE_ENTRY(b200s_cg_solve_device_f64, double, solve_device, false)
-B200S_SOLVE_ENTRY(b200s_bicgstab_solve_device_f64, double, solve_device, true)
+B200S_SOLVE_ENTRY_F64(b200s_cg_solve_device_f64, solve_device, false, true)
+B200S_SOLVE_ENTRY_F64(b200s_bicgstab_solve_device_f64, solve_device, true, true)
 B200S_SOLVE_ENTRY(b200s_cg_solve_device_f32, float, solve_device, false)
 B200S_SOLVE_ENTRY(b200s_bicgstab_solve_device_f32, float, solve_device, true)
 #undef B200S_SOLVE_ENTRY
+#undef B200S_SOLVE_ENTRY_F64
+
+// ---- incomplete factorizations (host analysis: csrc/factors.cpp; device application: precond.inc) ----
+#define B200S_NEW_FACTORS(CALL)                                  \
+  if (!out) return B200S_ERR_INVALID;                            \
+  *out = nullptr;                                                \
+  b200s_factors* f = new (std::nothrow) b200s_factors();         \
+  if (!f) return B200S_ERR_ALLOC;                                \
+  std::string err;                                               \
+  int rc = CALL;                                                 \
+  if (rc) {                                                      \
+    g_create_error = err;                                        \
+    delete f;                                                    \
+    return rc;                                                   \
+  }                                                              \
+  *out = f;                                                      \
+  return 0;
+
+int b200s_ilut_f64(int64_t n, const int32_t* rowptr, const int32_t* colidx, const double* values, double droptol,
+                   int fillfactor, const int32_t* perm, b200s_factors** out) {
+  B200S_NEW_FACTORS(ilut_factorize(n, rowptr, colidx, values, droptol, fillfactor, perm, f->f, err))
+}
+int b200s_ichol_f64(int64_t n, const int32_t* rowptr, const int32_t* colidx, const double* values, int uplo,
+                    double initial_shift, const int32_t* perm, b200s_factors** out) {
+  B200S_NEW_FACTORS(ichol_factorize(n, rowptr, colidx, values, uplo, initial_shift, perm, f->f, err))
+}
+int b200s_factors_from_ilut_f64(int64_t n, const int32_t* lu_rowptr, const int32_t* lu_colidx, const double* lu_values,
+                                const int32_t* perm, b200s_factors** out) {
+  B200S_NEW_FACTORS(factors_from_ilut(n, lu_rowptr, lu_colidx, lu_values, perm, f->f, err))
+}
+int b200s_factors_from_ichol_f64(int64_t n, const int32_t* colptr, const int32_t* rowidx, const double* l_values,
+                                 const double* scale, const int32_t* perm, b200s_factors** out) {
+  B200S_NEW_FACTORS(factors_from_ichol(n, colptr, rowidx, l_values, scale, perm, f->f, err))
+}
+#undef B200S_NEW_FACTORS
+void b200s_factors_destroy(b200s_factors* f) { delete f; }
+int b200s_factors_info(const b200s_factors* f) { return f ? f->f.info : 3; }
+int b200s_factors_kind(const b200s_factors* f) { return f ? f->f.kind : 0; }
+int64_t b200s_factors_size(const b200s_factors* f) { return f ? f->f.n : B200S_ERR_INVALID; }
+int64_t b200s_factors_nnz(const b200s_factors* f) { return f ? static_cast<int64_t>(f->f.inner.size()) : B200S_ERR_INVALID; }
+int64_t b200s_factors_perm_size(const b200s_factors* f) { return f ? static_cast<int64_t>(f->f.perm.size()) : B200S_ERR_INVALID; }
+int b200s_factors_get(const b200s_factors* f, int32_t* outer, int32_t* inner, double* values, double* scale, int32_t* perm) {
+  if (!f) return B200S_ERR_INVALID;
+  const Factors& F = f->f;
+  if (outer) std::copy(F.outer.begin(), F.outer.end(), outer);
+  if (inner) std::copy(F.inner.begin(), F.inner.end(), inner);
+  if (values) std::copy(F.vals.begin(), F.vals.end(), values);
+  if (scale) std::copy(F.scale.begin(), F.scale.end(), scale);
+  if (perm) std::copy(F.perm.begin(), F.perm.end(), perm);
+  return 0;
+}
+int b200s_factors_stage_sizes(const b200s_factors* f, int which, int64_t* nnz, int32_t* levels, int32_t* launches,
+                              int32_t* unit_diag, int32_t* fused) {
+  if (!f || which < 0 || which > 1) return B200S_ERR_INVALID;
+  const TriStage& s = which ? f->f.second : f->f.first;
+  if (nnz) *nnz = static_cast<int64_t>(s.colidx.size());
+  if (levels) *levels = s.level_ptr.empty() ? 0 : static_cast<int32_t>(s.level_ptr.size()) - 1;
+  if (launches) *launches = static_cast<int32_t>(s.launches.size());
+  if (unit_diag) *unit_diag = s.diag.empty() ? 1 : 0;
+  if (fused) *fused = s.fused ? 1 : 0;
+  return 0;
+}
+int b200s_factors_stage(const b200s_factors* f, int which, int32_t* rowptr, int32_t* colidx, double* values, double* diag,
+                        int32_t* level_ptr, int32_t* level_rows, int32_t* launches) {
+  if (!f || which < 0 || which > 1) return B200S_ERR_INVALID;
+  const TriStage& s = which ? f->f.second : f->f.first;
+  if (rowptr) std::copy(s.rowptr.begin(), s.rowptr.end(), rowptr);
+  if (colidx) std::copy(s.colidx.begin(), s.colidx.end(), colidx);
+  if (values) std::copy(s.vals.begin(), s.vals.end(), values);
+  if (diag) std::copy(s.diag.begin(), s.diag.end(), diag);
+  if (level_ptr) std::copy(s.level_ptr.begin(), s.level_ptr.end(), level_ptr);
+  if (level_rows) std::copy(s.level_rows.begin(), s.level_rows.end(), level_rows);
+  if (launches)
+    for (size_t i = 0; i < s.launches.size(); ++i) {
+      launches[3 * i] = s.launches[i].level_begin;
+      launches[3 * i + 1] = s.launches[i].level_end;
+      launches[3 * i + 2] = s.launches[i].rows;
+    }
+  return 0;
+}
+int b200s_factors_permscale(const b200s_factors* f, int32_t* pre_gather, double* pre_scale, int32_t* post_gather,
+                            double* post_scale, int32_t* present) {
+  if (!f) return B200S_ERR_INVALID;
+  const Factors& F = f->f;
+  if (pre_gather) std::copy(F.pre_gather.begin(), F.pre_gather.end(), pre_gather);
+  if (pre_scale) std::copy(F.pre_scale.begin(), F.pre_scale.end(), pre_scale);
+  if (post_gather) std::copy(F.post_gather.begin(), F.post_gather.end(), post_gather);
+  if (post_scale) std::copy(F.post_scale.begin(), F.post_scale.end(), post_scale);
+  if (present) {
+    present[0] = !F.pre_gather.empty();
+    present[1] = !F.pre_scale.empty();
+    present[2] = !F.post_gather.empty();
+    present[3] = !F.post_scale.empty();
+  }
+  return 0;
+}
+int b200s_set_preconditioner(b200s_handle* h, const b200s_factors* f) {
+  if (!h) return B200S_ERR_INVALID;
+  return set_factors(h, f ? &f->f : nullptr);
+}
+int b200s_precond_apply_f64(b200s_handle* h, const double* r, double* z) { return precond_apply_host(h, r, z); }
 
 int b200s_lscg_solve_f64(b200s_handle* hA, b200s_handle* hAt, const double* b, double* x, int use_guess, double tol,
                          int64_t max_iters, int precond, int colmajor_precond, int64_t* iters_out, double* error_out,

@@ -255,9 +255,15 @@ class _IterativeSolverBase(SparseOperator):
 
     _bicg = False
 
-    def __init__(self, A=None, uplo: int = Lower | Upper, preconditioner: int = DiagonalPreconditioner,
+    def __init__(self, A=None, uplo: int = Lower | Upper, preconditioner=DiagonalPreconditioner,
                  comm: Optional[Communicator] = None, **cfg):
-        self._precond = preconditioner
+        # preconditioner: IdentityPreconditioner / DiagonalPreconditioner, or an IncompleteLUT / IncompleteCholesky
+        # object (preconditioners.py) -- the template argument of the reference's solver classes
+        self._pre_obj = None
+        if not isinstance(preconditioner, (int, np.integer)):
+            self._pre_obj = preconditioner
+            preconditioner = DiagonalPreconditioner  # what factorize() builds underneath; replaced right after
+        self._precond = int(preconditioner)
         self._tolerance = -1.0                               # :413 -> NumTraits<Scalar>::epsilon(), resolved per dtype
         self._max_iterations = -1                            # :281-284 -> 2*cols
         self._iterations = 0
@@ -282,7 +288,27 @@ class _IterativeSolverBase(SparseOperator):
         super().factorize(A, self._precond if precond is None else precond)
         self._factorization_ok = True
         self._info = Success
+        if self._pre_obj is not None:
+            # IterativeSolverBase::factorize: m_preconditioner.factorize(matrix()); m_info = m_preconditioner.info()
+            # (IterativeSolverBase.h:216-224).  The factorization is host setup; the solves apply it on the GPU.
+            self._pre_obj.compute(A)
+            self._info = self._pre_obj.info()
+            if self._info == Success:
+                self._hd.check(self._hd.L.b200s_set_preconditioner(self._hd.h, self._pre_obj.handle()))
         return self
+
+    def preconditioner(self):
+        """The preconditioner object (IterativeSolverBase.h:249-253), or the enum value for Identity / Diagonal."""
+        return self._pre_obj if self._pre_obj is not None else self._precond
+
+    def precondition(self, r: np.ndarray) -> np.ndarray:
+        """z = preconditioner().solve(r) on the GPU (host vectors; for tests and diagnostics)."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        if r.shape != (self._rows,):
+            raise ValueError(f"r must have shape ({self._rows},)")
+        z = np.empty_like(r)
+        self._hd.check(self._hd.L.b200s_precond_apply_f64(self._hd.h, _ptr(r), _ptr(z)))
+        return z
 
     def compute(self, A, precond=None, inner_nnz=None):
         self.analyzePattern(A, inner_nnz)
@@ -436,8 +462,7 @@ class BiCGSTAB(_IterativeSolverBase):
     """BiCGSTAB<SparseMatrix<Scalar,RowMajor>, Preconditioner> (BiCGSTAB.h:157-208); the matrix is used as stored."""
     _bicg = True
 
-    def __init__(self, A=None, preconditioner: int = DiagonalPreconditioner, comm: Optional[Communicator] = None,
-                 **cfg):
+    def __init__(self, A=None, preconditioner=DiagonalPreconditioner, comm: Optional[Communicator] = None, **cfg):
         super().__init__(A, Lower | Upper, preconditioner, comm, **cfg)
 
 
@@ -445,7 +470,7 @@ class MINRES(_IterativeSolverBase):
     """MINRES<SparseMatrix<double>, UpLo, Preconditioner> (unsupported/Eigen/src/IterativeSolvers/MINRES.h:29-262) for
     self-adjoint operators; the default preconditioner is the identity, as in the reference.  One GPU, double."""
 
-    def __init__(self, A=None, uplo: int = Lower, preconditioner: int = IdentityPreconditioner, **cfg):
+    def __init__(self, A=None, uplo: int = Lower, preconditioner=IdentityPreconditioner, **cfg):
         super().__init__(A, uplo, preconditioner, None, **cfg)
 
     def _solve_vector(self, b, x, use_guess):
@@ -462,7 +487,7 @@ class GMRES(_IterativeSolverBase):
     Householder Arnoldi; set_restart / get_restart as in the reference (default 30).  One GPU, double."""
     _bicg = True
 
-    def __init__(self, A=None, preconditioner: int = DiagonalPreconditioner, **cfg):
+    def __init__(self, A=None, preconditioner=DiagonalPreconditioner, **cfg):
         self._restart = 30
         super().__init__(A, Lower | Upper, preconditioner, None, **cfg)
 

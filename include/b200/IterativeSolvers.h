@@ -73,6 +73,60 @@ template <>
 struct precond_id<Eigen::IdentityPreconditioner> {
   enum { supported = 1, value = B200S_PRECOND_IDENTITY };
 };
+// Incomplete factorizations (IncompleteLUT.h, IncompleteCholesky.h): the preconditioner object the solver owns computes
+// its factor on the host exactly as in the reference (IterativeSolverBase::compute calls m_preconditioner.compute,
+// IterativeSolverBase.h:196-247); the factor is then handed to the device, which applies it in every iteration
+// (b200s_set_preconditioner: level-scheduled triangular solves).  double only.
+template <typename Idx>
+struct precond_id<Eigen::IncompleteLUT<double, Idx> > {
+  enum { supported = 1, value = B200S_PRECOND_FACTORS };
+};
+template <int UpLo, typename Ordering>
+struct precond_id<Eigen::IncompleteCholesky<double, UpLo, Ordering> > {
+  enum { supported = 1, value = B200S_PRECOND_FACTORS };
+};
+
+// factors_of<P>::make: the b200s_factors object for what a preconditioner of the reference holds (0 = nothing to hand over)
+template <typename P>
+struct factors_of {
+  enum { has = 0 };
+  static b200s_factors* make(const P&) { return 0; }
+};
+template <typename Idx>
+struct factors_of<Eigen::IncompleteLUT<double, Idx> > {
+  enum { has = 1 };
+  typedef Eigen::IncompleteLUT<double, Idx> Pre;
+  // m_lu / m_P are protected (IncompleteLUT.h:183-189): pointers to members named through a derived class reach them
+  struct Peek : Pre {
+    static const typename Pre::FactorType& lu(const Pre& p) { return p.*(&Peek::m_lu); }
+    static const Eigen::PermutationMatrix<Eigen::Dynamic, Eigen::Dynamic, Idx>& perm(const Pre& p) { return p.*(&Peek::m_P); }
+  };
+  static b200s_factors* make(const Pre& pre) {
+    const typename Pre::FactorType& lu = Peek::lu(pre);
+    const Eigen::Index n = lu.rows(), nz = lu.outerIndexPtr()[n];
+    std::vector<int32_t> rp(lu.outerIndexPtr(), lu.outerIndexPtr() + n + 1), ci(lu.innerIndexPtr(), lu.innerIndexPtr() + nz);
+    const Idx* pi = Peek::perm(pre).indices().data();
+    std::vector<int32_t> perm(pi, pi + n);
+    b200s_factors* f = 0;
+    b200s_factors_from_ilut_f64(n, rp.data(), ci.data(), lu.valuePtr(), perm.data(), &f);
+    return f;
+  }
+};
+template <int UpLo, typename Ordering>
+struct factors_of<Eigen::IncompleteCholesky<double, UpLo, Ordering> > {
+  enum { has = 1 };
+  typedef Eigen::IncompleteCholesky<double, UpLo, Ordering> Pre;
+  static b200s_factors* make(const Pre& pre) {
+    const typename Pre::FactorType& L = pre.matrixL();
+    const Eigen::Index n = L.cols(), nz = L.outerIndexPtr()[n];
+    std::vector<int32_t> cp(L.outerIndexPtr(), L.outerIndexPtr() + n + 1), ri(L.innerIndexPtr(), L.innerIndexPtr() + nz);
+    const Eigen::Index ps = pre.permutationP().size();  // 0 for NaturalOrdering (IncompleteCholesky.h:100-102)
+    std::vector<int32_t> perm(pre.permutationP().indices().data(), pre.permutationP().indices().data() + ps);
+    b200s_factors* f = 0;
+    b200s_factors_from_ichol_f64(n, cp.data(), ri.data(), L.valuePtr(), pre.scalingS().data(), ps ? perm.data() : 0, &f);
+    return f;
+  }
+};
 
 // The C ABI entry points of one scalar type.
 template <typename S>
@@ -175,6 +229,12 @@ class DeviceSolver {
     return check(abi<Scalar>::factorize(m_handle, values, precond));
   }
 
+  // As above, then the preconditioner object's factor goes to the device (nothing to do for Jacobi / identity).
+  template <typename ActualMatrix, typename P>
+  bool factorize(const ActualMatrix& mat, int precond, const P& pre) {
+    return factorize_with(mat, precond, pre, Eigen::internal::bool_constant<bool(factors_of<P>::has)>());
+  }
+
   bool solve(bool bicg, const Scalar* b, Scalar* x, bool use_guess, double tol, Eigen::Index max_iters,
              Eigen::Index& iters, double& error, Eigen::ComputationInfo& info) {
     if (!m_handle) {
@@ -213,6 +273,23 @@ class DeviceSolver {
   }
 
  private:
+  template <typename ActualMatrix, typename P>
+  bool factorize_with(const ActualMatrix& mat, int precond, const P&, Eigen::internal::false_type) {
+    return factorize(mat, precond);
+  }
+  template <typename ActualMatrix, typename P>
+  bool factorize_with(const ActualMatrix& mat, int, const P& pre, Eigen::internal::true_type) {
+    if (!factorize(mat, B200S_PRECOND_JACOBI)) return false;
+    if (pre.info() != Eigen::Success) return true;  // the solver's info() already reports the failed factorization
+    b200s_factors* f = factors_of<P>::make(pre);
+    if (!f) {
+      m_error = b200s_last_error(0);
+      return false;
+    }
+    const bool ok = check(b200s_set_preconditioner(m_handle, f));
+    b200s_factors_destroy(f);
+    return ok;
+  }
   void reset() {
     if (m_handle) b200s_destroy(m_handle);
     m_handle = 0;
@@ -343,14 +420,14 @@ class ConjugateGradient : public Eigen::IterativeSolverBase<ConjugateGradient<Ma
   template <typename MatrixDerived>
   ConjugateGradient& factorize(const Eigen::EigenBase<MatrixDerived>& A) {
     Base::factorize(A.derived());
-    if (!m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value)) m_info = Eigen::InvalidInput;
+    if (!m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value, Base::m_preconditioner)) m_info = Eigen::InvalidInput;
     return *this;
   }
   template <typename MatrixDerived>
   ConjugateGradient& compute(const Eigen::EigenBase<MatrixDerived>& A) {
     Base::compute(A.derived());
     if (!m_dev.analyze(matrix(), int(UpLo), false) ||
-        !m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value))
+        !m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value, Base::m_preconditioner))
       m_info = Eigen::InvalidInput;
     return *this;
   }
@@ -459,14 +536,14 @@ class BiCGSTAB : public Eigen::IterativeSolverBase<BiCGSTAB<MatrixType_, Precond
     Base::factorize(A.derived());
     // a column-major input is converted to rows at analyze time; refresh that copy's values too
     if (!MatrixType::IsRowMajor && !m_dev.analyze(matrix(), B200S_BOTH, true)) m_info = Eigen::InvalidInput;
-    if (!m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value)) m_info = Eigen::InvalidInput;
+    if (!m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value, Base::m_preconditioner)) m_info = Eigen::InvalidInput;
     return *this;
   }
   template <typename MatrixDerived>
   BiCGSTAB& compute(const Eigen::EigenBase<MatrixDerived>& A) {
     Base::compute(A.derived());
     if (!m_dev.analyze(matrix(), B200S_BOTH, true) ||
-        !m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value))
+        !m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value, Base::m_preconditioner))
       m_info = Eigen::InvalidInput;
     return *this;
   }

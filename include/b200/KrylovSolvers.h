@@ -176,13 +176,13 @@ class MINRES : public Eigen::IterativeSolverBase<MINRES<MatrixType_, UpLo_, Prec
   template <typename MatrixDerived>
   MINRES& factorize(const Eigen::EigenBase<MatrixDerived>& A) {
     Base::factorize(A.derived());
-    if (!m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value)) m_info = Eigen::InvalidInput;
+    if (!m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value, Base::m_preconditioner)) m_info = Eigen::InvalidInput;
     return *this;
   }
   template <typename MatrixDerived>
   MINRES& compute(const Eigen::EigenBase<MatrixDerived>& A) {
     Base::compute(A.derived());
-    if (!m_dev.analyze(matrix(), int(UpLo), false) || !m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value))
+    if (!m_dev.analyze(matrix(), int(UpLo), false) || !m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value, Base::m_preconditioner))
       m_info = Eigen::InvalidInput;
     return *this;
   }
@@ -247,13 +247,13 @@ class GMRES : public Eigen::IterativeSolverBase<GMRES<MatrixType_, Preconditione
   GMRES& factorize(const Eigen::EigenBase<MatrixDerived>& A) {
     Base::factorize(A.derived());
     if (!MatrixType::IsRowMajor && !m_dev.analyze(matrix(), B200S_BOTH, true)) m_info = Eigen::InvalidInput;
-    if (!m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value)) m_info = Eigen::InvalidInput;
+    if (!m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value, Base::m_preconditioner)) m_info = Eigen::InvalidInput;
     return *this;
   }
   template <typename MatrixDerived>
   GMRES& compute(const Eigen::EigenBase<MatrixDerived>& A) {
     Base::compute(A.derived());
-    if (!m_dev.analyze(matrix(), B200S_BOTH, true) || !m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value))
+    if (!m_dev.analyze(matrix(), B200S_BOTH, true) || !m_dev.factorize(matrix(), detail::precond_id<Preconditioner>::value, Base::m_preconditioner))
       m_info = Eigen::InvalidInput;
     return *this;
   }

@@ -49,7 +49,9 @@ typedef enum {
 } b200s_status;
 
 enum { B200S_LOWER = 1, B200S_UPPER = 2, B200S_BOTH = 3 };
-enum { B200S_PRECOND_IDENTITY = 0, B200S_PRECOND_JACOBI = 1 };
+enum { B200S_PRECOND_IDENTITY = 0, B200S_PRECOND_JACOBI = 1,
+       B200S_PRECOND_FACTORS = 2 /* an incomplete factorization given to b200s_set_preconditioner */ };
+enum { B200S_FACTORS_ILUT = 1, B200S_FACTORS_ICHOL = 2 };
 enum { B200S_SPMV_AUTO = 0, B200S_SPMV_STAGED = 1, B200S_SPMV_DIRECT = 2 };
 enum {
   B200S_LOOP_AUTO = 0,
@@ -214,6 +216,61 @@ int b200s_minres_solve_f64(b200s_handle* h, const double* b, double* x, int use_
                            int64_t* iters_out, double* error_out, int* info_out);
 int b200s_gmres_solve_f64(b200s_handle* h, const double* b, double* x, int use_guess, double tol, int64_t max_iters,
                           int64_t restart, int64_t* iters_out, double* error_out, int* info_out);
+
+/* ---- incomplete factorizations as preconditioners --------------------------------------------------
+ * IncompleteLUT (Eigen/src/IterativeLinearSolvers/IncompleteLUT.h:98-446) and IncompleteCholesky
+ * (IncompleteCholesky.h:40-388) for the solvers above.  What runs EVERY ITERATION -- z = M^-1 r: two sparse triangular
+ * solves between permutations / scalings (IncompleteLUT.h:171-176, IncompleteCholesky.h:149-157, TriangularSolver.h:26-134)
+ * -- runs on the GPU: the rows of each solve are grouped into dependency levels, one thread sums one row in the
+ * reference's order with the reference's roundings, so z has the bits of the reference as g++ -O3 builds it for x86-64 with FMA.
+ * The factorization is sequential by construction (row ii needs the finished rows < ii) and is setup work: it is done
+ * once per matrix on the host, either by the restatements b200s_ilut_f64 / b200s_ichol_f64 (same factors as the
+ * reference, entry for entry, for the same permutation) or by the caller (b200s_factors_from_*: the C++ binding hands
+ * over what an Eigen::IncompleteLUT / IncompleteCholesky object computed).  These host functions are GPU-free.
+ *   perm : the fill-reducing permutation as the reference stores it -- IncompleteLUT::m_P.indices() resp.
+ *          IncompleteCholesky::m_perm.indices() -- or NULL for the natural ordering.  The reference obtains it from
+ *          AMDOrdering (an ordering heuristic, outside this path); any permutation is valid.
+ *   b200s_ilut_f64  : droptol < 0 -> 1e-12, fillfactor <= 0 -> 10 (the reference's defaults, IncompleteLUT.h:117-118).
+ *   b200s_ichol_f64 : uplo = the triangle of the CSR input that is read (LOWER or UPPER); initial_shift < 0 -> 1e-3.
+ *   b200s_factors_info : Eigen's ComputationInfo of the factorization (0 Success, 1 NumericalIssue).
+ * b200s_set_preconditioner (one GPU, double, after factorize) uploads the factors; from then on cg / bicgstab / minres /
+ * gmres solves of the handle precondition with them (CG and BiCGSTAB then run ConjugateGradient.h:26-91 / BiCGSTAB.h:28-107
+ * statement by statement on the device primitives, scalar recurrences on the host, because a triangular solve cannot be
+ * fused into their vector passes).  NULL returns to the preconditioner factorize built; factorize / analyze_pattern drop
+ * the factors (the matrix changed).  b200s_precond_apply_f64: z = M^-1 r for host vectors. */
+typedef struct b200s_factors b200s_factors;
+int b200s_ilut_f64(int64_t n, const int32_t* rowptr, const int32_t* colidx, const double* values, double droptol,
+                   int fillfactor, const int32_t* perm, b200s_factors** out);
+int b200s_ichol_f64(int64_t n, const int32_t* rowptr, const int32_t* colidx, const double* values, int uplo,
+                    double initial_shift, const int32_t* perm, b200s_factors** out);
+/* lu_*: IncompleteLUT::m_lu (row-major; per row: lower part, diagonal, upper part, each in any order) */
+int b200s_factors_from_ilut_f64(int64_t n, const int32_t* lu_rowptr, const int32_t* lu_colidx, const double* lu_values,
+                                const int32_t* perm, b200s_factors** out);
+/* colptr / rowidx / l_values: IncompleteCholesky::matrixL() (column-major lower); scale: scalingS() or NULL */
+int b200s_factors_from_ichol_f64(int64_t n, const int32_t* colptr, const int32_t* rowidx, const double* l_values,
+                                 const double* scale, const int32_t* perm, b200s_factors** out);
+void b200s_factors_destroy(b200s_factors* f);
+int b200s_factors_info(const b200s_factors* f);
+int b200s_factors_kind(const b200s_factors* f);          /* B200S_FACTORS_* */
+int64_t b200s_factors_size(const b200s_factors* f);      /* n */
+int64_t b200s_factors_nnz(const b200s_factors* f);       /* stored entries of m_lu / m_L */
+int64_t b200s_factors_perm_size(const b200s_factors* f); /* n, or 0 for IncompleteCholesky with the natural ordering */
+/* The factor as the reference stores it: outer (n+1), inner / values (nnz), scale (n, ICHOL), perm (perm_size). */
+int b200s_factors_get(const b200s_factors* f, int32_t* outer, int32_t* inner, double* values, double* scale, int32_t* perm);
+int b200s_set_preconditioner(b200s_handle* h, const b200s_factors* f);
+int b200s_precond_apply_f64(b200s_handle* h, const double* r, double* z);
+/* GPU-free view of what the device runs, for host-logic tests: stage 0 / 1 = first / second triangular solve.  Row i of a
+ * stage: t = x[i]; t -= values[k] * x[colidx[k]] over its entries in order (one FMA per step when `fused`, else product
+ * and subtraction rounded separately -- whichever the reference's compiled loop does); x[i] = unit_diag ? t : t / diag[i].
+ * level_rows[level_ptr[l] .. level_ptr[l+1]) are the rows of level l; launches holds (level_begin, level_end, widest
+ * level) per kernel launch.  permscale: x[k] = pre_scale[k] * r[pre_gather[k]] before, z[k] = post_scale[k] *
+ * x[post_gather[k]] after; present[0..3] says which of the four arrays exist (absent gather = identity, scale = 1). */
+int b200s_factors_stage_sizes(const b200s_factors* f, int which, int64_t* nnz, int32_t* levels, int32_t* launches,
+                              int32_t* unit_diag, int32_t* fused);
+int b200s_factors_stage(const b200s_factors* f, int which, int32_t* rowptr, int32_t* colidx, double* values, double* diag,
+                        int32_t* level_ptr, int32_t* level_rows, int32_t* launches);
+int b200s_factors_permscale(const b200s_factors* f, int32_t* pre_gather, double* pre_scale, int32_t* post_gather,
+                            double* post_scale, int32_t* present);
 
 /* ---- introspection --------------------------------------------------------------------------------------------- */
 int b200s_get_stats(b200s_handle* h, b200s_stats* out /* out->struct_size must be set */);

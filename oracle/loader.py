@@ -81,6 +81,10 @@ class Port:
             getattr(L, f"oracle_bicgstab_{sfx}").restype = None
         L.oracle_true_residual_f64.argtypes = [C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p]
         L.oracle_true_residual_f64.restype = C.c_double
+        L.oracle_tri_stage_f64.argtypes = [C.c_int64, _i32p, _i32p, _f64p, C.c_void_p, _i32p, C.c_int, _f64p]
+        L.oracle_tri_stage_f64.restype = None
+        L.oracle_permute_scale_f64.argtypes = [C.c_int64, _f64p, C.c_void_p, C.c_void_p, _f64p]
+        L.oracle_permute_scale_f64.restype = None
 
     @staticmethod
     def _sfx(a):
@@ -134,6 +138,31 @@ class Port:
         """Restarts (BiCGSTAB.h:72-81) taken by the last bicgstab() call of this port."""
         return int(C.c_int64.in_dll(self.lib, "oracle_last_restarts").value)
 
+    def factors_apply(self, pre, r, order="level", fused=None):
+        """z = M^-1 r with the stages of an IncompleteLUT / IncompleteCholesky object of the product
+        (eigen_git_mirror_b200.preconditioners), on the CPU.  order "level": rows in the device's level order;
+        "natural": the reference's sequential substitution order.  fused: None = as each stage says, or a bool /
+        pair of bools to override (probing what the reference's compiled loops do)."""
+        n = pre.rows()
+        pg, ps, qg, qs = pre.permscale()
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        keep = [np.ascontiguousarray(a) if a is not None else None for a in (pg, ps, qg, qs)]
+        x = np.empty(n)
+        self.lib.oracle_permute_scale_f64(n, np.ascontiguousarray(r, np.float64), vp(keep[0]), vp(keep[1]), x)
+        for which in (0, 1):
+            st = pre.stage(which)
+            if order == "level":
+                rows = np.ascontiguousarray(st.level_rows, np.int32)
+            else:
+                rows = np.arange(n, dtype=np.int32) if which == 0 else np.arange(n - 1, -1, -1, dtype=np.int32)
+            dg = None if st.diag is None else np.ascontiguousarray(st.diag)
+            fu = st.fused if fused is None else (fused[which] if isinstance(fused, (tuple, list)) else fused)
+            self.lib.oracle_tri_stage_f64(n, st.rowptr, np.ascontiguousarray(st.colidx), np.ascontiguousarray(st.vals),
+                                          vp(dg), rows, int(fu), x)
+        z = np.empty(n)
+        self.lib.oracle_permute_scale_f64(n, x, vp(keep[2]), vp(keep[3]), z)
+        return z
+
     def true_residual(self, A, x, b):
         return self.lib.oracle_true_residual_f64(A.rows, A.rowptr, A.colidx, A.vals.astype(np.float64),
                                                  np.ascontiguousarray(x, np.float64),
@@ -171,6 +200,18 @@ class Ref:
                                             C.c_int64, C.c_int, C.c_int, ip64, dp, ip]
             L.eigref_gmres_f64.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int, C.c_double,
                                            C.c_int64, C.c_int64, C.c_int, ip64, dp, ip]
+        if hasattr(L, "eigref_ilut_f64"):
+            csr = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p]
+            L.eigref_ilut_f64.argtypes = csr + [C.c_double, C.c_int, _i32p, _i32p, _f64p, C.c_int64, _i32p, _i32p, ip]
+            L.eigref_ilut_f64.restype = C.c_int64
+            L.eigref_ilut_solve_f64.argtypes = csr + [C.c_double, C.c_int, _f64p, _f64p]
+            L.eigref_ichol_f64.argtypes = csr + [C.c_int, C.c_int, C.c_double, _i32p, _i32p, _f64p, C.c_int64, _f64p,
+                                                 _i32p, ip, ip]
+            L.eigref_ichol_f64.restype = C.c_int64
+            L.eigref_ichol_solve_f64.argtypes = csr + [C.c_int, C.c_int, C.c_double, _f64p, _f64p]
+            L.eigref_precond_solver_f64.argtypes = [C.c_int] + csr + [_f64p, _f64p, C.c_int, C.c_double, C.c_int64,
+                                                                      C.c_int, C.c_int, C.c_double, C.c_int, C.c_int64,
+                                                                      ip64, dp, ip]
         L.eigref_symv_f64.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int]
         L.eigref_jacobi_f64.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p]
 
@@ -246,6 +287,56 @@ class Ref:
         return self._krylov(self.lib.eigref_gmres_f64, A, b, x0, A.rows,
                             lambda bb, x: (A.rows, A.nnz, A.rowptr, A.colidx, A.vals, bb, x, int(x0 is not None), tol,
                                            max_iters, restart, precond))
+
+
+    # ---- IncompleteLUT / IncompleteCholesky of the unmodified reference ----
+    def ilut(self, A, droptol=-1.0, fillfactor=0):
+        """(lu_rowptr, lu_colidx, lu_vals, P, Pinv, info): m_lu, m_P, m_Pinv of IncompleteLUT<double>(A)."""
+        n = A.rows
+        rp, P, Pinv, info = np.zeros(n + 1, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32), C.c_int(0)
+        cap = 1
+        while True:
+            ci, va = np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+            nz = self.lib.eigref_ilut_f64(n, A.nnz, A.rowptr, A.colidx, A.vals, droptol, fillfactor, rp, ci, va, cap, P,
+                                          Pinv, C.byref(info))
+            if nz <= cap:
+                return rp, ci[:nz].copy(), va[:nz].copy(), P, Pinv, info.value
+            cap = int(nz)
+
+    def ilut_solve(self, A, r, droptol=-1.0, fillfactor=0):
+        z = np.zeros(A.rows)
+        self.lib.eigref_ilut_solve_f64(A.rows, A.nnz, A.rowptr, A.colidx, A.vals, droptol, fillfactor,
+                                       np.ascontiguousarray(r, np.float64), z)
+        return z
+
+    def ichol(self, A, uplo=LOWER, ordering=0, shift=-1.0):
+        """(L_colptr, L_rowidx, L_vals, scale, perm, info): m_L, m_scale, m_perm (empty = natural ordering)."""
+        n = A.rows
+        cp, scale, perm = np.zeros(n + 1, np.int32), np.zeros(n), np.zeros(max(n, 1), np.int32)
+        psz, info = C.c_int(0), C.c_int(0)
+        cap = 1
+        while True:
+            ri, va = np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+            nz = self.lib.eigref_ichol_f64(n, A.nnz, A.rowptr, A.colidx, A.vals, uplo, ordering, shift, cp, ri, va, cap,
+                                           scale, perm, C.byref(psz), C.byref(info))
+            assert nz >= 0
+            if nz <= cap:
+                return cp, ri[:nz].copy(), va[:nz].copy(), scale, perm[:psz.value].copy(), info.value
+            cap = int(nz)
+
+    def ichol_solve(self, A, r, uplo=LOWER, ordering=0, shift=-1.0):
+        z = np.zeros(A.rows)
+        self.lib.eigref_ichol_solve_f64(A.rows, A.nnz, A.rowptr, A.colidx, A.vals, uplo, ordering, shift,
+                                        np.ascontiguousarray(r, np.float64), z)
+        return z
+
+    def precond_solver(self, which, A, b, x0=None, tol=-1.0, max_iters=-1, uplo=LOWER, ordering=1, droptol=-1.0,
+                       fillfactor=0, restart=0):
+        """which: "cg_ichol", "bicgstab_ilut" or "gmres_ilut" -- the reference's solver with that preconditioner."""
+        code = {"cg_ichol": 0, "bicgstab_ilut": 1, "gmres_ilut": 2}[which]
+        return self._krylov(self.lib.eigref_precond_solver_f64, A, b, x0, A.rows,
+                            lambda bb, x: (code, A.rows, A.nnz, A.rowptr, A.colidx, A.vals, bb, x, int(x0 is not None),
+                                           tol, max_iters, uplo, ordering, droptol, fillfactor, restart))
 
 
 _port = None

@@ -57,3 +57,35 @@ double oracle_true_residual_f64(int64_t n, const int32_t* rowptr, const int32_t*
   }
   return den > 0 ? sqrt(num / den) : sqrt(num);
 }
+
+/* ---- incomplete-factorization preconditioners ----------------------------------------------
+ * The reference applies IncompleteLUT / IncompleteCholesky with sequential substitutions (SparseCore/
+ * TriangularSolver.h:26-134).  oracle_tri_stage restates ONE such substitution in the row-wise form the device uses
+ * (eigen-git-mirror_b200/csrc/kernels_tri.cuh): row i: t = x[i]; t -= vals[k] * x[colidx[k]] over the row's entries in
+ * storage order; x[i] = diag ? t / diag[i] : t.  Rows are visited in the order `order` lists them (n entries): the
+ * natural order (ascending for a lower, descending for an upper factor) IS the reference's loop; the device's level
+ * order must give the same bits because a row only reads rows of earlier levels.  fused != 0: each step is one FMA
+ * -- what g++ -O3 emits for the column sweep `other.coeffRef(it.index(),col) -= tmp * it.value()` (:129) with FMA
+ * available; fused == 0: product and subtraction rounded separately -- what it emits for the row-wise loops
+ * `tmp -= lastVal * other.coeff(lastIndex,col)` (:49, :91).  Both probed against oracle/_ref (tests/test_factors.py). */
+void oracle_tri_stage_f64(int64_t n, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                          const double* diag, const int32_t* order, int fused, double* x) {
+  for (int64_t s = 0; s < n; ++s) {
+    const int32_t i = order[s];
+    double t = x[i];
+    for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      if (fused) t = fma(-vals[k], x[colidx[k]], t);
+      else t = t - vals[k] * x[colidx[k]];
+    }
+    x[i] = diag ? t / diag[i] : t;
+  }
+}
+
+/* out[k] = scale[k] * in[gather[k]]  (NULL gather = identity, NULL scale = 1): the permutation / scaling steps of
+ * IncompleteLUT.h:172,175 and IncompleteCholesky.h:152-156 as the device performs them. */
+void oracle_permute_scale_f64(int64_t n, const double* in, const int32_t* gather, const double* scale, double* out) {
+  for (int64_t k = 0; k < n; ++k) {
+    const double v = in[gather ? gather[k] : k];
+    out[k] = scale ? scale[k] * v : v;
+  }
+}

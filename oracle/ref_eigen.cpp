@@ -9,6 +9,7 @@
 //   DiagonalPreconditioner / Identity        Eigen/src/IterativeLinearSolvers/BasicPreconditioners.h:35-108,200-222
 //   LeastSquaresConjugateGradient            Eigen/src/IterativeLinearSolvers/LeastSquareConjugateGradient.h
 //   MINRES / GMRES                           unsupported/Eigen/src/IterativeSolvers/MINRES.h, GMRES.h
+//   IncompleteLUT / IncompleteCholesky       Eigen/src/IterativeLinearSolvers/IncompleteLUT.h, IncompleteCholesky.h
 // on caller-owned CSR arrays bound zero-copy through Map<const SparseMatrix> (SparseMap.h:270).
 //
 // Used for (1) pinning the C restatement in oracle/oracle.c, (2) generating tests/golden/*,
@@ -25,6 +26,7 @@
 #endif
 
 using namespace Eigen;
+#define COMMA ,
 
 namespace {
 
@@ -128,6 +130,51 @@ int spmv_impl(int64_t rows, int64_t cols, int64_t nnz, const int* rowptr, const 
   }
   if (best_seconds) *best_seconds = best;
   return 0;
+}
+
+
+// ---- incomplete factorizations as preconditioners ----------------------------------------------
+// IncompleteLUT keeps its factor and permutations protected (IncompleteLUT.h:183-189): a derived class only re-exports
+// them, no code of the reference is replaced.
+struct IlutAccess : IncompleteLUT<double, int> {
+  const FactorType& lu() const { return m_lu; }
+  const PermutationMatrix<Dynamic, Dynamic, int>& P() const { return m_P; }
+  const PermutationMatrix<Dynamic, Dynamic, int>& Pinv() const { return m_Pinv; }
+};
+
+template <typename Pre>
+void ilut_params(Pre& pre, double droptol, int fillfactor) {
+  if (droptol >= 0) pre.setDroptol(droptol);
+  if (fillfactor > 0) pre.setFillfactor(fillfactor);
+}
+
+template <typename IC>
+int64_t ichol_export(const CsrMap<double>& A, double shift, int* colptr, int* rowidx, double* vals, int64_t cap,
+                     double* scale, int* perm, int* perm_size, int* info) {
+  IC ic;
+  if (shift >= 0) ic.setInitialShift(shift);
+  ic.compute(A);
+  *info = int(ic.info());
+  const auto& L = ic.matrixL();
+  const int64_t n = L.cols(), nz = L.nonZeros();
+  for (int64_t j = 0; j <= n; ++j) colptr[j] = L.outerIndexPtr()[j];
+  for (int64_t k = 0; k < std::min<int64_t>(cap, nz); ++k) { rowidx[k] = L.innerIndexPtr()[k]; vals[k] = L.valuePtr()[k]; }
+  for (int64_t j = 0; j < ic.scalingS().size(); ++j) scale[j] = ic.scalingS()[j];
+  *perm_size = int(ic.permutationP().size());
+  for (int64_t j = 0; j < ic.permutationP().size(); ++j) perm[j] = ic.permutationP().indices()[j];
+  return nz;
+}
+
+template <typename IC>
+int ichol_solve(const CsrMap<double>& A, double shift, int64_t n, const double* r, double* z) {
+  IC ic;
+  if (shift >= 0) ic.setInitialShift(shift);
+  ic.compute(A);
+  Map<const Vec<double>> rm(r, n);
+  Map<Vec<double>> zm(z, n);
+  Vec<double> out = ic.solve(rm);
+  zm = out;
+  return int(ic.info());
 }
 
 }  // namespace
@@ -285,6 +332,90 @@ int eigref_gmres_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colid
     if (restart > 0) s.set_restart(restart);
     return run_solver(s, A, n, b, x, use_guess, tol, max_iters, iters, error, info, &ts, &tv);
   }
+  return -1;
+}
+
+
+// ---- SURVEY 8f rank 4 ---------------------------------------------------------------------------------------------
+// IncompleteLUT<double>::compute on the row-major matrix: the factor m_lu (row-major, rows NOT sorted: L part, diagonal,
+// U part in QuickSplit order) and the AMD permutation m_P.  Returns nnz(m_lu).
+int64_t eigref_ilut_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals, double droptol,
+                        int fillfactor, int* lu_rowptr, int* lu_colidx, double* lu_vals, int64_t cap, int* P, int* Pinv,
+                        int* info) {
+  CsrMap<double> A(n, n, nnz, rowptr, colidx, vals);
+  IlutAccess pre;
+  ilut_params(pre, droptol, fillfactor);
+  pre.compute(A);
+  *info = int(pre.info());
+  const auto& lu = pre.lu();
+  const int64_t nz = lu.nonZeros();
+  for (int64_t i = 0; i <= n; ++i) lu_rowptr[i] = lu.outerIndexPtr()[i];
+  for (int64_t k = 0; k < std::min<int64_t>(cap, nz); ++k) { lu_colidx[k] = lu.innerIndexPtr()[k]; lu_vals[k] = lu.valuePtr()[k]; }
+  for (int64_t i = 0; i < n; ++i) { P[i] = pre.P().indices()[i]; Pinv[i] = pre.Pinv().indices()[i]; }
+  return nz;
+}
+// z = IncompleteLUT(A).solve(r)   (IncompleteLUT.h:171-176)
+int eigref_ilut_solve_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals, double droptol,
+                          int fillfactor, const double* r, double* z) {
+  CsrMap<double> A(n, n, nnz, rowptr, colidx, vals);
+  IncompleteLUT<double, int> pre;
+  ilut_params(pre, droptol, fillfactor);
+  pre.compute(A);
+  Map<const Vec<double>> rm(r, n);
+  Map<Vec<double>> zm(z, n);
+  Vec<double> out = pre.solve(rm);
+  zm = out;
+  return int(pre.info());
+}
+// IncompleteCholesky<double, UpLo, Ordering>::compute: m_L (column-major lower), m_scale, m_perm.  ordering 0 natural, 1 AMD.
+int64_t eigref_ichol_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals, int uplo,
+                         int ordering, double shift, int* colptr, int* rowidx, double* lvals, int64_t cap, double* scale,
+                         int* perm, int* perm_size, int* info) {
+  CsrMap<double> A(n, n, nnz, rowptr, colidx, vals);
+  if (uplo == Lower && ordering == 0) return ichol_export<IncompleteCholesky<double, Lower, NaturalOrdering<int>>>(A, shift, colptr, rowidx, lvals, cap, scale, perm, perm_size, info);
+  if (uplo == Lower && ordering == 1) return ichol_export<IncompleteCholesky<double, Lower, AMDOrdering<int>>>(A, shift, colptr, rowidx, lvals, cap, scale, perm, perm_size, info);
+  if (uplo == Upper && ordering == 0) return ichol_export<IncompleteCholesky<double, Upper, NaturalOrdering<int>>>(A, shift, colptr, rowidx, lvals, cap, scale, perm, perm_size, info);
+  if (uplo == Upper && ordering == 1) return ichol_export<IncompleteCholesky<double, Upper, AMDOrdering<int>>>(A, shift, colptr, rowidx, lvals, cap, scale, perm, perm_size, info);
+  return -1;
+}
+int eigref_ichol_solve_f64(int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals, int uplo,
+                           int ordering, double shift, const double* r, double* z) {
+  CsrMap<double> A(n, n, nnz, rowptr, colidx, vals);
+  if (uplo == Lower && ordering == 0) return ichol_solve<IncompleteCholesky<double, Lower, NaturalOrdering<int>>>(A, shift, n, r, z);
+  if (uplo == Lower && ordering == 1) return ichol_solve<IncompleteCholesky<double, Lower, AMDOrdering<int>>>(A, shift, n, r, z);
+  if (uplo == Upper && ordering == 0) return ichol_solve<IncompleteCholesky<double, Upper, NaturalOrdering<int>>>(A, shift, n, r, z);
+  if (uplo == Upper && ordering == 1) return ichol_solve<IncompleteCholesky<double, Upper, AMDOrdering<int>>>(A, shift, n, r, z);
+  return -1;
+}
+// Solvers with these preconditioners.  which: 0 ConjugateGradient<_, uplo, IncompleteCholesky<double, uplo or Lower, ordering>>,
+// 1 BiCGSTAB<_, IncompleteLUT>, 2 GMRES<_, IncompleteLUT>, 3 MINRES<_, uplo, IncompleteCholesky<...>> is not a reference
+// combination and is not offered.
+int eigref_precond_solver_f64(int which, int64_t n, int64_t nnz, const int* rowptr, const int* colidx, const double* vals,
+                              const double* b, double* x, int use_guess, double tol, int64_t max_iters, int uplo,
+                              int ordering, double droptol, int fillfactor, int64_t restart, int64_t* iters,
+                              double* error, int* info) {
+  CsrMap<double> A(n, n, nnz, rowptr, colidx, vals);
+  double ts, tv;
+#define EIGREF_RUN(SOLVER, SETUP)                                                                     \
+  {                                                                                                    \
+    SOLVER s;                                                                                          \
+    SETUP;                                                                                             \
+    return run_solver(s, A, n, b, x, use_guess, tol, max_iters, iters, error, info, &ts, &tv);         \
+  }
+  typedef Csr<double> M;
+  if (which == 0) {
+    if (uplo == Lower && ordering == 0) EIGREF_RUN(ConjugateGradient<M COMMA Lower COMMA IncompleteCholesky<double COMMA Lower COMMA NaturalOrdering<int>>>, (void)0)
+    if (uplo == Lower && ordering == 1) EIGREF_RUN(ConjugateGradient<M COMMA Lower COMMA IncompleteCholesky<double COMMA Lower COMMA AMDOrdering<int>>>, (void)0)
+    if (uplo == Upper && ordering == 0) EIGREF_RUN(ConjugateGradient<M COMMA Upper COMMA IncompleteCholesky<double COMMA Upper COMMA NaturalOrdering<int>>>, (void)0)
+    if (uplo == Upper && ordering == 1) EIGREF_RUN(ConjugateGradient<M COMMA Upper COMMA IncompleteCholesky<double COMMA Upper COMMA AMDOrdering<int>>>, (void)0)
+    if (uplo == (Lower | Upper) && ordering == 0) EIGREF_RUN(ConjugateGradient<M COMMA Lower | Upper COMMA IncompleteCholesky<double COMMA Lower COMMA NaturalOrdering<int>>>, (void)0)
+    if (uplo == (Lower | Upper) && ordering == 1) EIGREF_RUN(ConjugateGradient<M COMMA Lower | Upper COMMA IncompleteCholesky<double COMMA Lower COMMA AMDOrdering<int>>>, (void)0)
+  } else if (which == 1) {
+    EIGREF_RUN(BiCGSTAB<M COMMA IncompleteLUT<double>>, ilut_params(s.preconditioner(), droptol, fillfactor))
+  } else if (which == 2) {
+    EIGREF_RUN(GMRES<M COMMA IncompleteLUT<double>>, (ilut_params(s.preconditioner(), droptol, fillfactor), restart > 0 ? s.set_restart(restart) : (void)0))
+  }
+#undef EIGREF_RUN
   return -1;
 }
 
