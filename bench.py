@@ -18,7 +18,8 @@ its x after those iterations is compared with the GPU's x at the same maxIterati
 
 The headline line also carries `configs`: the other BASELINE.json configurations measured in the same run with the same
 protocol (extra keys; the headline keys are unchanged) -- at N=1 configs[2] (BiCGSTAB 256^3), configs[0] (2D 1024^2) and
-configs[3] (the SpMV sweep, see --sweep-rows); at N=8 configs[4] (512^3 CG).  --no-extras skips them.
+configs[3] (the SpMV sweep, see --sweep-rows) and IncompleteCholesky-preconditioned CG at 128^3; at N=8
+configs[4] (512^3 CG).  --no-extras skips them.
 """
 from __future__ import annotations
 
@@ -323,6 +324,52 @@ def multi_rhs_config(env, egm, n, cols, steps, peak):
     return out
 
 
+def precond_config(env, egm, n, steps):
+    """ConjugateGradient + IncompleteCholesky (natural ordering) on 3D Poisson n^3.  The factor is
+    computed once on the host (setup_s); every iteration applies it on the GPU as level-scheduled triangular solves.
+    Reported next to Jacobi-preconditioned CG on the same system: iterations and device time to the same tolerance."""
+    from eigen_git_mirror_b200 import workloads as wl
+    torch = env.torch
+    A = wl.poisson3d(n)
+    b = torch.from_numpy(np.asarray(A.to_scipy() @ wl.random_vector(A.rows, 12345))).cuda()
+    x = torch.zeros_like(b)
+    t0 = time.perf_counter()
+    pre = egm.IncompleteCholesky(uplo=egm.Lower)
+    s = egm.ConjugateGradient(A, preconditioner=pre, device=env.local_rank)
+    setup_s = time.perf_counter() - t0
+    s.setTolerance(TOL)
+    s.solve_device(b, x)  # warm-up
+    ms = 0.0
+    for _ in range(steps):
+        s.solve_device(b, x)
+        ms += s.stats()["last_solve_ms"]
+    st = s.stats()
+    it_ic, err_ic, info_ic = s.iterations(), s.error(), s.info()
+    s.precondition(wl.random_vector(A.rows, 777))
+    apply_ms, apply_launches = s.stats()["last_solve_ms"], int(s.stats()["last_kernel_launches"])
+    levels = [len(pre.stage(w).level_ptr) - 1 for w in (0, 1)]
+    factor_nnz = int(pre.L.b200s_factors_nnz(pre.handle()))
+    s.close()
+    j = egm.ConjugateGradient(A, device=env.local_rank)
+    j.setTolerance(TOL)
+    j.solve_device(b, x)
+    jms = 0.0
+    for _ in range(steps):
+        j.solve_device(b, x)
+        jms += j.stats()["last_solve_ms"]
+    out = {"workload": f"3D 7-point Poisson {n}^3, ConjugateGradient<double> + IncompleteCholesky<double, Lower, NaturalOrdering>, tol {TOL:g}",
+           "iterations": int(it_ic), "error": err_ic, "info": int(info_ic), "ms_per_solve": ms / steps,
+           "gpu_launches": int(st["last_kernel_launches"]), "host_factorization_and_setup_s": round(setup_s, 2),
+           "factor_nnz": factor_nnz, "levels": levels, "apply_ms": apply_ms, "apply_launches": apply_launches,
+           # both factors once (12 B per entry) + x gathered per entry + the vector in and out
+           "apply_gbs": (2 * factor_nnz * 20 + 4 * A.rows * 8) / (apply_ms * 1e-3) / 1e9 if apply_ms > 0 else None,
+           "jacobi_iterations": int(j.iterations()), "jacobi_ms_per_solve": jms / steps}
+    j.close()
+    del b, x
+    torch.cuda.empty_cache()
+    return out
+
+
 def spmv_sweep(env, egm, rows, peak, reps=20):
     """configs[3]: SpMV-only sweep on synthetic CSR, float and double, device-resident x / y, best of
     3 runs of `reps` back-to-back products after 5 warm-ups; GB/s = algorithmic bytes / time."""
@@ -490,6 +537,11 @@ def run_ours(args):
                 configs["poisson3d_512"] = side_config(env, egm, 512, "cg", 3, 3, 3, peak)
         except Exception as e:
             configs["error"] = repr(e)
+        if world == 1 and solver == "cg" and n == 256:
+            try:  # kept apart: a problem here must not hide the configurations above
+                configs["ichol_cg_128"] = precond_config(env, egm, 128, max(2, args.steps // 4))
+            except Exception as e:
+                configs["ichol_cg_128"] = {"error": repr(e)}
 
     if rank == 0:
         line = {
