@@ -8,6 +8,8 @@ real-matrix test flow (test/sparse_solver.h:147-179, bench/spbench/spbenchsolver
                           caller picks UpLo, as spbenchsolver does), duplicates are summed (setFromTriplets),
                           out-of-range entries are skipped with a warning.
 * ``saveMarket`` / ``loadMarketVector`` / ``saveMarketVector`` -- coordinate / array real, 17 significant digits.
+* ``MatrixMarketIterator`` -- the folder walk of SparseExtra/MatrixMarketIterator.h:41-241 (name.mtx, name_b.mtx,
+                          name_x.mtx, the "SPD" name convention), used by tools/solve_market.py.
 
 Host-side only (numpy); nothing here touches the GPU.
 """
@@ -124,3 +126,140 @@ def saveMarketVector(vec, filename: str) -> bool:
     except OSError:
         return False
     return True
+
+
+SPD, NonSymmetric = 0x100, 0x0
+
+
+class MatrixMarketIterator:
+    """MatrixMarketIterator<double> (unsupported/Eigen/src/SparseExtra/MatrixMarketIterator.h:41-241): walks a folder
+    of MatrixMarket files.  ``matname.mtx`` is a matrix, ``matname_b.mtx`` its right-hand side, ``matname_x.mtx`` a
+    reference solution; a symmetric file whose name contains "SPD" is flagged SPD (:222-224).  Usage as in the
+    reference::
+
+        it = MatrixMarketIterator(folder)
+        while it:
+            A, b = it.matrix(), it.rhs()
+            ...
+            it.next()
+    """
+
+    def __init__(self, folder: str):
+        import os
+        self._folder = folder
+        self._valid_folder = os.path.isdir(folder)
+        # readdir order is unspecified in the reference; sorted here so that runs are reproducible
+        self._entries = sorted(os.listdir(folder)) if self._valid_folder else []
+        self._pos = 0
+        self._reset()
+        self._isvalid = False
+        if self._valid_folder:
+            self._next_valid()
+
+    def _reset(self):
+        self._mat = None
+        self._rhs = None
+        self._refx = None
+        self._has_rhs = self._has_refx = False
+
+    def _next_valid(self):  # Getnextvalidmatrix, :193-227
+        import os
+        self._isvalid = False
+        while self._pos < len(self._entries):
+            name = self._entries[self._pos]
+            self._pos += 1
+            path = os.path.join(self._folder, name)
+            if os.path.isdir(path):
+                continue
+            ok, sym, iscomplex, isvector = getMarketHeader(path)
+            if not ok or isvector or iscomplex:   # Scalar = double: complex files are skipped (:205-214)
+                continue
+            if not name.endswith(".mtx"):
+                continue
+            self._matname = name[:-4]
+            self._sym = SPD if ("SPD" in self._matname and sym != NonSymmetric) else sym
+            self._isvalid = True
+            break
+
+    def __bool__(self):
+        return self._isvalid
+
+    def next(self):
+        """operator++ (:67-74)."""
+        self._reset()
+        self._next_valid()
+        return self
+
+    def matname(self) -> str:
+        return self._matname
+
+    def sym(self) -> int:
+        return self._sym
+
+    def isFolderValid(self) -> bool:
+        return self._valid_folder
+
+    def hasRhs(self) -> bool:
+        return self._has_rhs
+
+    def hasrefX(self) -> bool:
+        return self._has_refx
+
+    def matrix(self) -> CsrMatrix:
+        """:78-107: the matrix of the current file; a symmetric file that stores one triangle is expanded to the full
+        matrix (the test `lower_norm > diag_norm && upper_norm == diag_norm` of the reference, on the stored entries)."""
+        import os
+        if self._mat is not None:
+            return self._mat
+        A = loadMarket(os.path.join(self._folder, self._matname + ".mtx"))
+        if self._sym != NonSymmetric and A.rows == A.cols:
+            rowof = np.repeat(np.arange(A.rows), np.diff(A.rowptr))
+            d = np.sqrt(np.sum(A.vals[A.colidx == rowof] ** 2))
+            lo = np.sqrt(np.sum(A.vals[A.colidx <= rowof] ** 2))
+            up = np.sqrt(np.sum(A.vals[A.colidx >= rowof] ** 2))
+            if (lo > d and up == d) or (up > d and lo == d):
+                import scipy.sparse as sp
+                S = A.to_scipy()
+                S = (S + S.T - sp.diags(S.diagonal())).tocsr()
+                S.sort_indices()
+                A = CsrMatrix(A.rows, A.cols, S.indptr.astype(np.int32), S.indices.astype(np.int32),
+                              np.ascontiguousarray(S.data, np.float64), 0, A.name)
+        self._mat = A
+        return A
+
+    def rhs(self) -> np.ndarray:
+        """:112-133: matname_b.mtx if it exists, else b = A * refX for a random refX (uniform in [-1, 1], as setRandom)."""
+        import os
+        if self._has_rhs:
+            return self._rhs
+        path = os.path.join(self._folder, self._matname + "_b.mtx")
+        if os.path.exists(path):
+            try:
+                self._rhs = loadMarketVector(path)
+                self._has_rhs = True
+            except (ValueError, OSError):
+                self._has_rhs = False
+        if not self._has_rhs:
+            A = self.matrix()
+            rng = np.random.default_rng(abs(hash(self._matname)) % (1 << 32))
+            self._refx = rng.uniform(-1.0, 1.0, A.cols)
+            self._rhs = np.asarray(A.to_scipy() @ self._refx)
+            self._has_refx = True
+            self._has_rhs = True
+        return self._rhs
+
+    def refX(self) -> np.ndarray:
+        """:141-156: matname_x.mtx if it exists (or the random solution behind a generated rhs), else an empty vector."""
+        import os
+        if self._has_refx:
+            return self._refx
+        path = os.path.join(self._folder, self._matname + "_x.mtx")
+        if os.path.exists(path):
+            try:
+                self._refx = loadMarketVector(path)
+                self._has_refx = True
+            except (ValueError, OSError):
+                self._has_refx = False
+        if not self._has_refx:
+            self._refx = np.zeros(0)
+        return self._refx

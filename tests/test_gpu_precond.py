@@ -194,3 +194,33 @@ def test_reference_drivers_on_b200_solvers_with_incomplete_factorizations(seed, 
         pytest.skip(f"{exe} not built (needs /root/reference: make -C oracle conformance)")
     res = subprocess.run([exe, f"s{seed}", "r3"], capture_output=True, text=True, timeout=800)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_real_matrix_flow_on_a_folder_of_matrix_market_files(tmp_path, egm):
+    """The spbenchsolver-style flow (tools/solve_market.py, bench/spbench/spbenchsolver.h:213-300 in the reference): a
+    folder with an SPD matrix stored as one triangle and a general matrix with right-hand side and reference solution;
+    every solver of the tool's list must converge to the reference solution."""
+    import subprocess
+    import sys
+    import scipy.sparse as sp
+    from eigen_git_mirror_b200 import marketio as mio, workloads as wl
+    A = wl.poisson3d(14)
+    L = sp.tril(A.to_scipy()).tocsr()
+    mio.saveMarket(wl.CsrMatrix(A.rows, A.cols, L.indptr.astype(np.int32), L.indices.astype(np.int32), L.data),
+                   str(tmp_path / "lap_SPD.mtx"), sym=mio.Symmetric)
+    Cm = wl.convdiff3d(12)
+    x = wl.random_vector(Cm.rows, 4)
+    mio.saveMarket(Cm, str(tmp_path / "cd.mtx"))
+    mio.saveMarketVector(np.asarray(Cm.to_scipy() @ x), str(tmp_path / "cd_b.mtx"))
+    mio.saveMarketVector(x, str(tmp_path / "cd_x.mtx"))
+    out = tmp_path / "out"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "solve_market.py"), str(tmp_path), "--out", str(out)],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("info=0") == 8, res.stdout  # 5 solvers on the SPD matrix, 3 on the general one
+    for which in ("bicgstab", "bicgstab_ilut", "gmres_ilut"):
+        got = mio.loadMarketVector(str(out / f"cd_{which}_x.mtx"))
+        assert np.linalg.norm(got - x) <= 1e-7 * np.linalg.norm(x), which
+    xs = [mio.loadMarketVector(str(out / f"lap_SPD_{w}_x.mtx")) for w in ("cg", "cg_ic", "bicgstab", "bicgstab_ilut", "gmres_ilut")]
+    for v in xs[1:]:
+        assert np.linalg.norm(v - xs[0]) <= 1e-7 * np.linalg.norm(xs[0])
