@@ -325,31 +325,43 @@ def multi_rhs_config(env, egm, n, cols, steps, peak):
 
 
 def precond_config(env, egm, n, steps):
-    """ConjugateGradient + IncompleteCholesky (natural ordering) on 3D Poisson n^3.  The factor is
-    computed once on the host (setup_s); every iteration applies it on the GPU as level-scheduled triangular solves.
-    Reported next to Jacobi-preconditioned CG on the same system: iterations and device time to the same tolerance."""
+    """ConjugateGradient + IncompleteCholesky on 3D Poisson n^3.  The factor is computed once on the
+    host; every iteration applies it on the GPU as level-scheduled triangular solves.  Two orderings: natural (the
+    reference's NaturalOrdering instantiation: ~3n narrow dependency levels, launch-latency-bound) and multi-colour
+    (b200s_ordering_multicolor: red-black here, 2 wide levels per solve, more iterations).  Reported next to
+    Jacobi-preconditioned CG on the same system: iterations and device time to the same tolerance."""
     from eigen_git_mirror_b200 import workloads as wl
     torch = env.torch
     A = wl.poisson3d(n)
     b = torch.from_numpy(np.asarray(A.to_scipy() @ wl.random_vector(A.rows, 12345))).cuda()
     x = torch.zeros_like(b)
-    t0 = time.perf_counter()
-    pre = egm.IncompleteCholesky(uplo=egm.Lower)
-    s = egm.ConjugateGradient(A, preconditioner=pre, device=env.local_rank)
-    setup_s = time.perf_counter() - t0
-    s.setTolerance(TOL)
-    s.solve_device(b, x)  # warm-up
-    ms = 0.0
-    for _ in range(steps):
-        s.solve_device(b, x)
-        ms += s.stats()["last_solve_ms"]
-    st = s.stats()
-    it_ic, err_ic, info_ic = s.iterations(), s.error(), s.info()
-    s.precondition(wl.random_vector(A.rows, 777))
-    apply_ms, apply_launches = s.stats()["last_solve_ms"], int(s.stats()["last_kernel_launches"])
-    levels = [len(pre.stage(w).level_ptr) - 1 for w in (0, 1)]
-    factor_nnz = int(pre.L.b200s_factors_nnz(pre.handle()))
-    s.close()
+    out = {"workload": f"3D 7-point Poisson {n}^3, ConjugateGradient<double> + IncompleteCholesky<double, Lower>, tol {TOL:g}"}
+    for ordering in ("natural", "multicolor"):
+        t0 = time.perf_counter()
+        perm, colours = (None, 0) if ordering == "natural" else egm.multicolor_ordering(A)
+        pre = egm.IncompleteCholesky(uplo=egm.Lower, perm=perm)
+        s = egm.ConjugateGradient(A, preconditioner=pre, device=env.local_rank)
+        setup_s = time.perf_counter() - t0
+        s.setTolerance(TOL)
+        s.solve_device(b, x)  # warm-up
+        ms = 0.0
+        for _ in range(steps):
+            s.solve_device(b, x)
+            ms += s.stats()["last_solve_ms"]
+        st = s.stats()
+        res = {"iterations": int(s.iterations()), "error": s.error(), "info": int(s.info()), "ms_per_solve": ms / steps,
+               "gpu_launches": int(st["last_kernel_launches"]), "host_factorization_and_setup_s": round(setup_s, 2),
+               "factor_nnz": int(pre.L.b200s_factors_nnz(pre.handle())), "colours": colours,
+               "levels": [len(pre.stage(w).level_ptr) - 1 for w in (0, 1)]}
+        s.precondition(wl.random_vector(A.rows, 777))
+        s.precondition(wl.random_vector(A.rows, 777))
+        res["apply_ms"] = s.stats()["last_solve_ms"]
+        res["apply_launches"] = int(s.stats()["last_kernel_launches"])
+        # both factors once (12 B per entry) + x gathered per entry (8 B) + the vector in and out of each of the 4 passes
+        res["apply_gbs"] = ((2 * res["factor_nnz"] * 20 + 8 * A.rows * 8) / (res["apply_ms"] * 1e-3) / 1e9
+                            if res["apply_ms"] > 0 else None)
+        out[ordering] = res
+        s.close()
     j = egm.ConjugateGradient(A, device=env.local_rank)
     j.setTolerance(TOL)
     j.solve_device(b, x)
@@ -357,13 +369,7 @@ def precond_config(env, egm, n, steps):
     for _ in range(steps):
         j.solve_device(b, x)
         jms += j.stats()["last_solve_ms"]
-    out = {"workload": f"3D 7-point Poisson {n}^3, ConjugateGradient<double> + IncompleteCholesky<double, Lower, NaturalOrdering>, tol {TOL:g}",
-           "iterations": int(it_ic), "error": err_ic, "info": int(info_ic), "ms_per_solve": ms / steps,
-           "gpu_launches": int(st["last_kernel_launches"]), "host_factorization_and_setup_s": round(setup_s, 2),
-           "factor_nnz": factor_nnz, "levels": levels, "apply_ms": apply_ms, "apply_launches": apply_launches,
-           # both factors once (12 B per entry) + x gathered per entry + the vector in and out
-           "apply_gbs": (2 * factor_nnz * 20 + 4 * A.rows * 8) / (apply_ms * 1e-3) / 1e9 if apply_ms > 0 else None,
-           "jacobi_iterations": int(j.iterations()), "jacobi_ms_per_solve": jms / steps}
+    out["jacobi"] = {"iterations": int(j.iterations()), "ms_per_solve": jms / steps}
     j.close()
     del b, x
     torch.cuda.empty_cache()

@@ -17,9 +17,9 @@ from . import solvers  # noqa: F401
 from .solvers import (GMRES, MINRES, BiCGSTAB, Communicator, ConjugateGradient, DiagonalPreconditioner,  # noqa: F401
                       IdentityPreconditioner, InvalidInput, LeastSquaresConjugateGradient, Lower, NoConvergence,
                       NumericalIssue, SparseOperator, Success, Upper, device_count, partition_rows)
-from .preconditioners import IncompleteCholesky, IncompleteLUT  # noqa: F401
+from .preconditioners import IncompleteCholesky, IncompleteLUT, multicolor_ordering  # noqa: F401
 from ._lib import B200Error  # noqa: F401
 
 __all__ = ["ConjugateGradient", "BiCGSTAB", "LeastSquaresConjugateGradient", "MINRES", "GMRES", "SparseOperator", "Communicator", "partition_rows", "device_count",
            "Lower", "Upper", "Success", "NumericalIssue", "NoConvergence", "InvalidInput", "DiagonalPreconditioner",
-           "IdentityPreconditioner", "IncompleteLUT", "IncompleteCholesky", "B200Error", "workloads"]
+           "IdentityPreconditioner", "IncompleteLUT", "IncompleteCholesky", "multicolor_ordering", "B200Error", "workloads"]

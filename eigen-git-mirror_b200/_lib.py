@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     L.b200s_ichol_f64.argtypes = csr + [C.c_int, dbl, vp, C.POINTER(F)]
     L.b200s_factors_from_ilut_f64.argtypes = csr + [vp, C.POINTER(F)]
     L.b200s_factors_from_ichol_f64.argtypes = csr + [vp, vp, C.POINTER(F)]
+    L.b200s_ordering_multicolor.argtypes = [i64, vp, vp, vp]
     L.b200s_factors_destroy.argtypes = [F]
     L.b200s_factors_destroy.restype = None
     for name in ("info", "kind"):

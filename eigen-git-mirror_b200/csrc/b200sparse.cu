@@ -1511,6 +1511,12 @@ int b200s_factors_from_ichol_f64(int64_t n, const int32_t* colptr, const int32_t
   B200S_NEW_FACTORS(factors_from_ichol(n, colptr, rowidx, l_values, scale, perm, f->f, err))
 }
 #undef B200S_NEW_FACTORS
+int b200s_ordering_multicolor(int64_t n, const int32_t* rowptr, const int32_t* colidx, int32_t* perm) {
+  std::string err;
+  int rc = multicolor_ordering(n, rowptr, colidx, perm, err);
+  if (rc < 0) g_create_error = err;
+  return rc;
+}
 void b200s_factors_destroy(b200s_factors* f) { delete f; }
 int b200s_factors_info(const b200s_factors* f) { return f ? f->f.info : 3; }
 int b200s_factors_kind(const b200s_factors* f) { return f ? f->f.kind : 0; }

@@ -203,6 +203,45 @@ int stages_from_l(Factors& f, std::string& err) {
 
 }  // namespace
 
+int multicolor_ordering(int64_t n, const int32_t* rowptr, const int32_t* colidx, int32_t* perm, std::string& err) {
+  if (n < 0 || (n > 0 && (!rowptr || !colidx || !perm))) { err = "ordering: null or negative argument"; return B200S_ERR_INVALID; }
+  // symmetrised adjacency (pattern of A + A^T without the diagonal)
+  std::vector<int64_t> ptr(static_cast<size_t>(n) + 1, 0);
+  for (int64_t i = 0; i < n; ++i)
+    for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      const int64_t j = colidx[k];
+      if (j < 0 || j >= n) { err = "ordering: column index out of range"; return B200S_ERR_INVALID; }
+      if (j != i) { ptr[i + 1]++; ptr[j + 1]++; }
+    }
+  for (int64_t i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
+  std::vector<int32_t> adj(static_cast<size_t>(ptr[n]));
+  {
+    std::vector<int64_t> cur(ptr.begin(), ptr.end() - 1);
+    for (int64_t i = 0; i < n; ++i)
+      for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int64_t j = colidx[k];
+        if (j != i) { adj[cur[i]++] = static_cast<int32_t>(j); adj[cur[j]++] = static_cast<int32_t>(i); }
+      }
+  }
+  std::vector<int32_t> colour(static_cast<size_t>(n), -1), mark;
+  int32_t ncol = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    mark.assign(static_cast<size_t>(ncol) + 1, 0);
+    for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k)
+      if (colour[adj[k]] >= 0) mark[colour[adj[k]]] = 1;
+    int32_t c = 0;
+    while (mark[c]) ++c;
+    colour[i] = c;
+    ncol = std::max(ncol, c + 1);
+  }
+  // stable counting sort by colour: new position of vertex i
+  std::vector<int64_t> start(static_cast<size_t>(ncol) + 1, 0);
+  for (int64_t i = 0; i < n; ++i) start[colour[i] + 1]++;
+  for (int32_t c = 0; c < ncol; ++c) start[c + 1] += start[c];
+  for (int64_t i = 0; i < n; ++i) perm[i] = static_cast<int32_t>(start[colour[i]]++);
+  return ncol;
+}
+
 int factors_from_ilut(int64_t n, const int32_t* lu_rowptr, const int32_t* lu_colidx, const double* lu_vals,
                       const int32_t* perm, Factors& f, std::string& err) {
   if (n < 0 || (n > 0 && (!lu_rowptr || !lu_colidx || !lu_vals))) { err = "factors: null or negative argument"; return B200S_ERR_INVALID; }

@@ -38,6 +38,20 @@ class Stage:
     fused: bool = False          # each step one FMA (else product and subtraction rounded separately)
 
 
+def multicolor_ordering(A):
+    """Permutation with few, wide dependency levels for the GPU's triangular solves: greedy multi-colouring of the
+    pattern of A + A^T, rows sorted by colour (b200s_ordering_multicolor; host, GPU-free).  Returns (perm, colours);
+    perm is what IncompleteLUT / IncompleteCholesky take as ``perm``."""
+    from .solvers import _as_csr
+    A = _as_csr(A)
+    perm = np.zeros(A.rows, np.int32)
+    L = _lib.lib()
+    nc = L.b200s_ordering_multicolor(A.rows, _ptr(A.rowptr), _ptr(A.colidx), _ptr(perm))
+    if nc < 0:
+        raise B200Error(nc, L.b200s_last_error(None).decode())
+    return perm, int(nc)
+
+
 class _Factors:
     """Owns one b200s_factors object."""
 

@@ -243,6 +243,12 @@ int b200s_ilut_f64(int64_t n, const int32_t* rowptr, const int32_t* colidx, cons
                    int fillfactor, const int32_t* perm, b200s_factors** out);
 int b200s_ichol_f64(int64_t n, const int32_t* rowptr, const int32_t* colidx, const double* values, int uplo,
                     double initial_shift, const int32_t* perm, b200s_factors** out);
+/* An ordering for the GPU rather than for fill: greedy multi-colouring of the pattern of A + A^T, rows sorted by colour
+ * (host, GPU-free).  Rows of one colour are not coupled, so the triangular solves of a zero-fill factor have one
+ * dependency level per colour (red-black on the 5/7-point stencils: 2 wide levels instead of ~3n narrow ones) at the
+ * price of some extra iterations.  perm (n entries) is in the convention of the functions above; returns the number of
+ * colours or a negative status. */
+int b200s_ordering_multicolor(int64_t n, const int32_t* rowptr, const int32_t* colidx, int32_t* perm);
 /* lu_*: IncompleteLUT::m_lu (row-major; per row: lower part, diagonal, upper part, each in any order) */
 int b200s_factors_from_ilut_f64(int64_t n, const int32_t* lu_rowptr, const int32_t* lu_colidx, const double* lu_values,
                                 const int32_t* perm, b200s_factors** out);

@@ -225,3 +225,39 @@ def test_argument_errors():
         IncompleteLUT.from_factors(np.array([0, 1, 2], np.int32), np.array([1, 0], np.int32), np.array([1.0, 1.0]))
     with pytest.raises(AssertionError):
         IncompleteLUT().info()
+
+
+def test_multicolor_ordering_gives_few_wide_levels():
+    """b200s_ordering_multicolor: a valid permutation (reference convention) that groups rows by colour; no two coupled
+    rows share a colour; red-black on the 7-point stencil, so the incomplete-Cholesky solves have 2 levels instead of ~3n."""
+    from eigen_git_mirror_b200.preconditioners import multicolor_ordering
+    for A, want in ((wl.poisson3d(12), 2), (wl.poisson2d(17), 2), (_random_square(400, 0.02, 21, symmetric=True), None)):
+        perm, nc = multicolor_ordering(A)
+        assert np.array_equal(np.sort(perm), np.arange(A.rows))
+        if want:
+            assert nc == want
+        S = A.to_scipy()
+        S = (abs(S) + abs(S.T)).tocoo()
+        off = S.row != S.col
+        # colour of a vertex = the colour block its new position falls into: recover block boundaries from the ordering
+        order = np.argsort(perm)                      # order[k] = old row at new position k
+        P = sp.csr_matrix((np.ones(A.rows), (perm, np.arange(A.rows))), shape=(A.rows, A.rows))
+        B = (P @ (abs(A.to_scipy()) + abs(A.to_scipy().T)) @ P.T).tocsr()
+        B.setdiag(0)
+        B.eliminate_zeros()
+        # rows of one colour are contiguous and mutually uncoupled: greedy level analysis of the lower part of B (every
+        # row one level above its deepest coupled predecessor) must give exactly nc levels
+        level = np.zeros(A.rows, np.int64)
+        for i in range(A.rows):
+            cols = B.indices[B.indptr[i]:B.indptr[i + 1]]
+            cols = cols[cols < i]
+            if cols.size:
+                level[i] = level[cols].max() + 1
+        assert level.max() + 1 <= nc and np.all(np.diff(level) >= 0), "colour blocks must be contiguous and uncoupled"
+        assert off.any()
+    A = wl.poisson3d(12)
+    perm, _ = multicolor_ordering(A)
+    g = IncompleteCholesky(A, uplo=1, perm=perm)
+    assert g.info() == 0 and [len(g.stage(w).level_ptr) - 1 for w in (0, 1)] == [2, 2]
+    nat = IncompleteCholesky(A, uplo=1)
+    assert len(nat.stage(0).level_ptr) - 1 == 3 * 12 - 2

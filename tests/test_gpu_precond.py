@@ -224,3 +224,34 @@ def test_real_matrix_flow_on_a_folder_of_matrix_market_files(tmp_path, egm):
     xs = [mio.loadMarketVector(str(out / f"lap_SPD_{w}_x.mtx")) for w in ("cg", "cg_ic", "bicgstab", "bicgstab_ilut", "gmres_ilut")]
     for v in xs[1:]:
         assert np.linalg.norm(v - xs[0]) <= 1e-7 * np.linalg.norm(xs[0])
+
+
+def test_multicolor_ordering_two_wide_levels(egm, port):
+    """An ordering for the GPU (b200s_ordering_multicolor): red-black on the 7-point stencil, so each triangular solve is
+    2 grid-wide levels instead of ~3n narrow ones.  Same kernels, same bits as the CPU emulation of the staged solves;
+    CG converges to the same solution as with the natural ordering."""
+    from eigen_git_mirror_b200 import workloads as wl
+    A = wl.poisson3d(40)
+    xt = wl.random_vector(A.rows, 12345)
+    b = np.asarray(A.to_scipy() @ xt)
+    perm, colours = egm.multicolor_ordering(A)
+    assert colours == 2
+    pre = egm.IncompleteCholesky(uplo=egm.Lower, perm=perm)
+    s = egm.ConjugateGradient(A, preconditioner=pre)
+    assert [len(pre.stage(w).level_ptr) - 1 for w in (0, 1)] == [2, 2]
+    r = wl.random_vector(A.rows, 5)
+    z = s.precondition(r)
+    assert s.stats()["last_kernel_launches"] == 2 + len(pre.stage(0).launches) + len(pre.stage(1).launches) == 6
+    assert np.array_equal(z, port.factors_apply(pre, r))
+    s.setTolerance(1e-10)
+    x = s.solve(b)
+    assert s.info() == egm.Success and np.linalg.norm(x - xt) <= 1e-8 * np.linalg.norm(xt)
+    nat = egm.ConjugateGradient(A, preconditioner=egm.IncompleteCholesky(uplo=egm.Lower))
+    nat.setTolerance(1e-10)
+    nat.solve(b)
+    jac = egm.ConjugateGradient(A)
+    jac.setTolerance(1e-10)
+    jac.solve(b)
+    assert nat.iterations() <= s.iterations() < jac.iterations(), (nat.iterations(), s.iterations(), jac.iterations())
+    for t in (s, nat, jac):
+        t.close()
