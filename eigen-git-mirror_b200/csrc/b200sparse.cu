@@ -1485,7 +1485,13 @@ B200S_SOLVE_ENTRY(b200s_bicgstab_solve_device_f32, float, solve_device, true)
   b200s_factors* f = new (std::nothrow) b200s_factors();         \
   if (!f) return B200S_ERR_ALLOC;                                \
   std::string err;                                               \
-  int rc = CALL;                                                 \
+  int rc;                                                        \
+  try {                                                          \
+    rc = CALL;                                                   \
+  } catch (const std::bad_alloc&) { /* no exception crosses the C boundary */ \
+    rc = B200S_ERR_ALLOC;                                        \
+    err = "host allocation failed while factorizing";           \
+  }                                                              \
   if (rc) {                                                      \
     g_create_error = err;                                        \
     delete f;                                                    \
@@ -1513,7 +1519,13 @@ int b200s_factors_from_ichol_f64(int64_t n, const int32_t* colptr, const int32_t
 #undef B200S_NEW_FACTORS
 int b200s_ordering_multicolor(int64_t n, const int32_t* rowptr, const int32_t* colidx, int32_t* perm) {
   std::string err;
-  int rc = multicolor_ordering(n, rowptr, colidx, perm, err);
+  int rc;
+  try {
+    rc = multicolor_ordering(n, rowptr, colidx, perm, err);
+  } catch (const std::bad_alloc&) {
+    rc = B200S_ERR_ALLOC;
+    err = "host allocation failed while ordering";
+  }
   if (rc < 0) g_create_error = err;
   return rc;
 }

@@ -329,8 +329,10 @@ int ilut_factorize(int64_t n, const int32_t* rowptr, const int32_t* colidx, cons
   f.outer.assign(1, 0);
   f.inner.clear();
   f.vals.clear();
-  f.inner.reserve(static_cast<size_t>(n * (nnzL + nnzU + 1)));
-  f.vals.reserve(static_cast<size_t>(n * (nnzL + nnzU + 1)));
+  // the reference reserves n * (nnzL + nnzU + 1) (:276), an upper bound that is gigabytes beyond need for large n; the
+  // vectors grow on demand here, a modest reservation only avoids the first reallocations
+  f.inner.reserve(static_cast<size_t>(std::min<int64_t>(n * (nnzL + nnzU + 1), 2 * nnz_a + n)));
+  f.vals.reserve(f.inner.capacity());
   std::vector<int32_t> diag_pos(static_cast<size_t>(n), 0);  // where row i of the factor holds its diagonal
   f.info = 0;
 
