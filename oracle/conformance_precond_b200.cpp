@@ -15,6 +15,7 @@
 
 #include <b200/IterativeSolvers.h>
 #include <b200/KrylovSolvers.h>
+#include <b200/Ordering.h>
 
 namespace {
 
@@ -31,6 +32,11 @@ void incomplete_cholesky_suite() {
   CALL_SUBTEST(check_sparse_spd_solving(cg_illt_upper_amd));
   CALL_SUBTEST(check_sparse_spd_solving(cg_illt_upper_nat));
   CALL_SUBTEST(check_sparse_spd_solving(cg_illt_uplo_amd));
+  // the ordering made for the GPU (include/b200/Ordering.h) in the same slot as AMDOrdering / NaturalOrdering
+  b200::ConjugateGradient<SparseMatrixType, Lower, IncompleteCholesky<T, Lower, b200::MulticolorOrdering<I_> > > cg_illt_lower_mc;
+  b200::ConjugateGradient<SparseMatrixType, Upper, IncompleteCholesky<T, Upper, b200::MulticolorOrdering<I_> > > cg_illt_upper_mc;
+  CALL_SUBTEST(check_sparse_spd_solving(cg_illt_lower_mc));
+  CALL_SUBTEST(check_sparse_spd_solving(cg_illt_upper_mc));
 }
 
 void bug1150() {  // test/incomplete_cholesky.cpp:34-61
