@@ -32,7 +32,12 @@ void incomplete_cholesky_suite() {
   CALL_SUBTEST(check_sparse_spd_solving(cg_illt_upper_amd));
   CALL_SUBTEST(check_sparse_spd_solving(cg_illt_upper_nat));
   CALL_SUBTEST(check_sparse_spd_solving(cg_illt_uplo_amd));
-  // the ordering made for the GPU (include/b200/Ordering.h) in the same slot as AMDOrdering / NaturalOrdering
+}
+
+// the ordering made for the GPU (include/b200/Ordering.h) in the same slot as AMDOrdering / NaturalOrdering
+template <typename T, typename I_>
+void multicolor_suite() {
+  typedef SparseMatrix<T, 0, I_> SparseMatrixType;
   b200::ConjugateGradient<SparseMatrixType, Lower, IncompleteCholesky<T, Lower, b200::MulticolorOrdering<I_> > > cg_illt_lower_mc;
   b200::ConjugateGradient<SparseMatrixType, Upper, IncompleteCholesky<T, Upper, b200::MulticolorOrdering<I_> > > cg_illt_upper_mc;
   CALL_SUBTEST(check_sparse_spd_solving(cg_illt_lower_mc));
@@ -71,6 +76,12 @@ void ilut_suite() {
 
 }  // namespace
 
+#ifdef B200_CONFORMANCE_ORDERING_ONLY  // built as its own binary (conformance_ordering_b200)
+EIGEN_DECLARE_TEST(b200_multicolor_ordering) {
+  CALL_SUBTEST_1((multicolor_suite<double, int>()));
+  CALL_SUBTEST_1((multicolor_suite<double, long int>()));
+}
+#else
 EIGEN_DECLARE_TEST(b200_incomplete_cholesky) {
   CALL_SUBTEST_1((incomplete_cholesky_suite<double, int>()));
   CALL_SUBTEST_1((incomplete_cholesky_suite<double, long int>()));
@@ -83,3 +94,4 @@ EIGEN_DECLARE_TEST(b200_ilut) {
   b200::GMRES<SparseMatrix<double>, IncompleteLUT<double> > gmres_colmajor_ilut;
   CALL_SUBTEST_1(check_sparse_square_solving(gmres_colmajor_ilut));
 }
+#endif

@@ -255,3 +255,15 @@ def test_multicolor_ordering_two_wide_levels(egm, port):
     assert nat.iterations() <= s.iterations() < jac.iterations(), (nat.iterations(), s.iterations(), jac.iterations())
     for t in (s, nat, jac):
         t.close()
+
+
+@pytest.mark.parametrize("seed", [42])
+def test_reference_driver_with_the_multicolor_ordering_functor(seed, egm):
+    """oracle/_ref/conformance_ordering_b200: check_sparse_spd_solving on b200::ConjugateGradient with
+    IncompleteCholesky<double, UpLo, b200::MulticolorOrdering> (include/b200/Ordering.h)."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "conformance_ordering_b200")
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs /root/reference: make -C oracle conformance)")
+    res = subprocess.run([exe, f"s{seed}", "r3"], capture_output=True, text=True, timeout=800)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
