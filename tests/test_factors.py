@@ -261,3 +261,53 @@ def test_multicolor_ordering_gives_few_wide_levels():
     assert g.info() == 0 and [len(g.stage(w).level_ptr) - 1 for w in (0, 1)] == [2, 2]
     nat = IncompleteCholesky(A, uplo=1)
     assert len(nat.stage(0).level_ptr) - 1 == 3 * 12 - 2
+
+
+def test_random_matrices_fuzz(ref3, port):
+    """40 random systems (sizes 2..120, densities 2-40 %, explicit zeros, random droptol / fillfactor): factors and staged
+    applies bit for bit as the reference's, for ILUT (reference's AMD permutation) and IC (Lower and Upper, AMD)."""
+    rng = np.random.default_rng(0)
+
+    def mk(S):
+        S = S.tocsr()
+        S.sort_indices()
+        return wl.CsrMatrix(S.shape[0], S.shape[1], S.indptr.astype(np.int32), S.indices.astype(np.int32),
+                            S.data.astype(np.float64))
+
+    for t in range(40):
+        n = int(rng.integers(2, 120))
+        S = sp.random(n, n, density=float(rng.uniform(0.02, 0.4)), random_state=rng, format="csr")
+        S.data = rng.standard_normal(S.nnz)
+        if t % 3 == 0 and S.nnz:
+            S.data[rng.integers(0, S.nnz, size=max(1, S.nnz // 10))] = 0.0   # stored zeros stay entries, as in Eigen
+        S = S + sp.diags(np.asarray(abs(S).sum(axis=1)).ravel() + rng.uniform(0.1, 2, n))
+        A = mk(S)
+        dt, ff = (-1.0, 0) if t % 2 else (float(10 ** rng.uniform(-6, -1)), int(rng.integers(1, 30)))
+        rp, ci, va, P, _, info = ref3.ilut(A, dt, ff)
+        f = IncompleteLUT(A, dt, ff, perm=P)
+        outer, inner, vals, _, _ = f.arrays()
+        assert f.info() == info and np.array_equal(outer, rp) and np.array_equal(inner, ci) and np.array_equal(vals, va), t
+        r = rng.standard_normal(n)
+        if info == 0:
+            assert np.array_equal(port.factors_apply(f, r), ref3.ilut_solve(A, r, dt, ff)), t
+        Asym = mk((S + S.T) * 0.5)
+        for uplo in (1, 2):
+            cp, ri, lv, sc, perm, info = ref3.ichol(Asym, uplo, 1)
+            g = IncompleteCholesky(Asym, uplo=uplo, perm=perm)
+            assert g.info() == info, t
+            if info == 0:
+                outer, inner, vals, scale, _ = g.arrays()
+                assert np.array_equal(outer, cp) and np.array_equal(inner, ri) and np.array_equal(vals, lv), t
+                assert np.array_equal(scale, sc) and np.array_equal(port.factors_apply(g, r), ref3.ichol_solve(Asym, r, uplo, 1)), t
+
+
+def test_degenerate_sizes(ref3, port):
+    for dense in ([[2.5]], [[4.0, 1.0], [1.0, 3.0]]):
+        S = sp.csr_matrix(np.array(dense))
+        A = wl.CsrMatrix(S.shape[0], S.shape[1], S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data.copy())
+        r = np.arange(1, A.rows + 1, dtype=np.float64)
+        *_, P, _, _ = ref3.ilut(A)
+        assert np.array_equal(port.factors_apply(IncompleteLUT(A, perm=P), r), ref3.ilut_solve(A, r))
+        assert np.array_equal(port.factors_apply(IncompleteCholesky(A, uplo=1), r), ref3.ichol_solve(A, r, 1, 0))
+    E = wl.CsrMatrix(0, 0, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    assert IncompleteLUT(E).info() == 0 and IncompleteCholesky(E, uplo=1).info() == 0
