@@ -241,7 +241,8 @@ class MatrixMarketIterator:
                 self._has_rhs = False
         if not self._has_rhs:
             A = self.matrix()
-            rng = np.random.default_rng(abs(hash(self._matname)) % (1 << 32))
+            import zlib
+            rng = np.random.default_rng(zlib.crc32(self._matname.encode()))  # reproducible per matrix name
             self._refx = rng.uniform(-1.0, 1.0, A.cols)
             self._rhs = np.asarray(A.to_scipy() @ self._refx)
             self._has_refx = True
