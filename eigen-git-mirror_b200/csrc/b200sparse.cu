@@ -1592,7 +1592,11 @@ int b200s_factors_permscale(const b200s_factors* f, int32_t* pre_gather, double*
 }
 int b200s_set_preconditioner(b200s_handle* h, const b200s_factors* f) {
   if (!h) return B200S_ERR_INVALID;
-  return set_factors(h, f ? &f->f : nullptr);
+  try {
+    return set_factors(h, f ? &f->f : nullptr);
+  } catch (const std::bad_alloc&) {  // no exception crosses the C boundary
+    return fail(h, B200S_ERR_ALLOC, "set_preconditioner: host allocation failed");
+  }
 }
 int b200s_precond_apply_f64(b200s_handle* h, const double* r, double* z) { return precond_apply_host(h, r, z); }
 
