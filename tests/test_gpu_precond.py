@@ -267,3 +267,42 @@ def test_reference_driver_with_the_multicolor_ordering_functor(seed, egm):
         pytest.skip(f"{exe} not built (needs /root/reference: make -C oracle conformance)")
     res = subprocess.run([exe, f"s{seed}", "r3"], capture_output=True, text=True, timeout=800)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_incomplete_cholesky_cg_at_baseline_size_vs_reference_fixture(egm):
+    """BASELINE.json's 3D Poisson 256^3 (16.7 M unknowns) with ConjugateGradient + IncompleteCholesky<double, Lower,
+    NaturalOrdering> against the UNMODIFIED reference run on exactly this input (tests/golden/fullsize_v2.npz,
+    make_fullsize_v2.py: 239 iterations, 166 s on the CPU): fixed-k trajectories identical in count with x to 1e-9, the
+    converged solve within the north-star bars (iterations within 2 %, x within 1e-8), true residual below tol."""
+    from eigen_git_mirror_b200 import workloads as wl
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fullsize_v2.npz"))
+    case = "cg_ichol_256"
+    A = wl.poisson3d(256)
+    assert A.rows == int(z[f"{case}/rows"]) and A.nnz == int(z[f"{case}/nnz"])
+    xt = wl.random_vector(A.rows, 12345)
+    b = wl.rhs_from_solution(A, xt)
+    idx = z[f"{case}/sample_idx"]
+    pre = egm.IncompleteCholesky(uplo=egm.Lower)
+    s = egm.ConjugateGradient(A, preconditioner=pre)
+    assert s.info() == egm.Success
+    s.setTolerance(1e-10)
+    for tag in ("k1", "k5", "k20", "full"):
+        s.setMaxIterations(int(tag[1:]) if tag != "full" else -1)
+        x = s.solve(b)
+        itr, errr, infor = int(z[f"{case}/{tag}/iters"]), float(z[f"{case}/{tag}/error"]), int(z[f"{case}/{tag}/info"])
+        ref = z[f"{case}/{tag}/x_samples"]
+        rel = np.linalg.norm(x[idx] - ref) / np.linalg.norm(ref)
+        xn = float(z[f"{case}/{tag}/xnorm"])
+        if tag == "full":
+            assert s.info() == infor == 0 and abs(s.iterations() - itr) <= max(1, 0.02 * itr), (s.iterations(), itr)
+            # same count => same trajectory up to rounding; one iteration more or less moves x by about its own error
+            bar = 1e-8 if s.iterations() == itr else 1e-7
+            assert s.error() <= 1e-10 and rel <= bar and abs(np.linalg.norm(x) - xn) <= bar * xn, (rel, s.error())
+        else:
+            assert s.iterations() == itr and s.info() == infor, (tag, s.iterations(), itr)
+            assert abs(s.error() - errr) <= 1e-6 * errr and rel <= 1e-9, (tag, s.error(), errr, rel)
+    op = egm.SparseOperator(A)
+    r = b - op.multiply(x)
+    assert np.linalg.norm(r) <= 1.05e-10 * np.linalg.norm(b)
+    op.close()
+    s.close()
