@@ -491,11 +491,13 @@ def run_ours(args):
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     it_bytes = iteration_bytes(nnz_global, rows_global, solver)
     it_gbs = it_bytes * iters_total / (dev_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None  # DRAM bytes per launch from the committed ncu --set full capture (not re-measured here)
     tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"poisson3d_{n}_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get(f"poisson3d_{n}_bytes_per_launch")
+            traffic_src = tj.get("source") if traffic is not None else None
         except Exception:
             traffic = None
 
@@ -567,7 +569,7 @@ def run_ours(args):
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm", "kernel": "spmv_staged_kernel<double> (CSR SpMV, y = A p)",
                          "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": spmv_bytes,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": spmv_bytes,
                          "ms_per_launch": spmv_ms},
             "spmv": {"gbs": achieved, "frac_of_hbm": achieved / (peak * world), "ms": spmv_ms},
             "iteration": {"bytes": it_bytes, "gbs": it_gbs, "frac_of_hbm": it_gbs / (peak * world),
