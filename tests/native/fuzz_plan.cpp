@@ -1,7 +1,7 @@
 // tests/native/fuzz_plan.cpp -- TEST INFRASTRUCTURE (CPU): one stored triangle on a ROW-PARTITIONED matrix
 // (csrc/plan.cpp: canonicalise_distributed, exchange_mirror_values) under AddressSanitizer + UBSan.  W = 2..4 "ranks" are
 // threads of one process with a barrier-based all-gather; random symmetric matrices, uneven partitions incl. empty
-// ranks, Lower and Upper; every rank must end up with exactly its rows of the full matrix (pattern and values).
+// ranks, Lower, Upper and fully stored; every rank must end up with exactly its rows of the full matrix (pattern and values).
 // Built and run by tests/test_native_fuzz.py.
 #include "plan.h"
 #include <pthread.h>
@@ -36,7 +36,7 @@ int main() {
     std::vector<int64_t> starts(W + 1, 0);
     for (int q = 1; q < W; ++q) starts[q] = std::min<int64_t>(n, starts[q - 1] + rng() % (2 * n / W + 1));
     starts[W] = n; std::sort(starts.begin(), starts.end());
-    for (int uplo = 1; uplo <= 2; ++uplo) {
+    for (int uplo = 1; uplo <= 3; ++uplo) {  // 3 = both triangles stored: the plain row-block plan
       Comm comm; comm.W = W; pthread_barrier_init(&comm.bar, nullptr, W);
       std::vector<int> fails(W, 0);
       std::vector<std::thread> th;
@@ -45,7 +45,7 @@ int main() {
         b200s_config cfg; std::memset(&cfg, 0, sizeof(cfg)); cfg.struct_size = sizeof(cfg); cfg.rank = r; cfg.world = W; cfg.allgather = ag; cfg.allgather_ctx = &ctx;
         const int64_t lo = starts[r], hi = starts[r + 1], rows = hi - lo;
         std::vector<int32_t> rp(rows + 1, 0), ci; std::vector<double> va;
-        for (int64_t i = lo; i < hi; ++i) { for (int j = 0; j < n; ++j) if (M[i][j] != 0 && (uplo == 1 ? j <= i : j >= i)) { ci.push_back(j); va.push_back(M[i][j]); } rp[i - lo + 1] = (int32_t)ci.size(); }
+        for (int64_t i = lo; i < hi; ++i) { for (int j = 0; j < n; ++j) if (M[i][j] != 0 && (uplo == 3 || (uplo == 1 ? j <= i : j >= i))) { ci.push_back(j); va.push_back(M[i][j]); } rp[i - lo + 1] = (int32_t)ci.size(); }
         Plan p; std::string err;
         int rc = build_plan(cfg, rows, n, (int64_t)ci.size(), rp.data(), ci.data(), nullptr, uplo, starts.data(), p, err);
         std::vector<unsigned char> imp;
@@ -55,8 +55,8 @@ int main() {
         for (int64_t il = 0; il < rows; ++il) {
           std::vector<double> row(n, 0.0);
           for (int32_t k = p.rowptr[il]; k < p.rowptr[il + 1]; ++k) {
-            int32_t lc = p.colidx[k]; int64_t gc = lc < rows ? lo + lc : p.ghost_cols[lc - rows];
-            int64_t s = p.src[k]; row[gc] += s < p.input_nnz ? va[s] : im[s - p.input_nnz];
+            int32_t lc = p.colidx_ptr()[k]; int64_t gc = lc < rows ? lo + lc : p.ghost_cols[lc - rows];
+            int64_t s = p.src.empty() ? k : p.src[k]; row[gc] += s < p.input_nnz ? va[s] : im[s - p.input_nnz];
           }
           for (int j = 0; j < n; ++j) if (row[j] != M[lo + il][j]) { fails[r] = 1; }
         }
