@@ -54,6 +54,14 @@ def build_ref(reference="/root/reference"):
     return False
 
 
+class _OracleFactors(C.Structure):
+    """oracle.c: oracle_factors."""
+    _fields_ = [("n", C.c_int64), ("pre_gather", C.c_void_p), ("pre_scale", C.c_void_p), ("post_gather", C.c_void_p),
+                ("post_scale", C.c_void_p), ("rowptr", C.c_void_p * 2), ("colidx", C.c_void_p * 2),
+                ("vals", C.c_void_p * 2), ("diag", C.c_void_p * 2), ("order", C.c_void_p * 2), ("fused", C.c_int32 * 2),
+                ("work", C.c_void_p)]
+
+
 class Port:
     def __init__(self):
         path = os.path.join(HERE, "_build", "liboracle.so")
@@ -85,6 +93,14 @@ class Port:
         L.oracle_tri_stage_f64.restype = None
         L.oracle_permute_scale_f64.argtypes = [C.c_int64, _f64p, C.c_void_p, C.c_void_p, _f64p]
         L.oracle_permute_scale_f64.restype = None
+        L.oracle_cg_factors_f64.argtypes = [C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_double, C.c_int64, C.c_int,
+                                            C.c_int, C.POINTER(_OracleFactors), C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.oracle_cg_factors_f64.restype = None
+        L.oracle_bicgstab_factors_f64.argtypes = [C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_double, C.c_int64,
+                                                  C.c_int, C.POINTER(_OracleFactors), C.POINTER(C.c_int64),
+                                                  C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.oracle_bicgstab_factors_f64.restype = None
 
     @staticmethod
     def _sfx(a):
@@ -162,6 +178,57 @@ class Port:
         z = np.empty(n)
         self.lib.oracle_permute_scale_f64(n, x, vp(keep[2]), vp(keep[3]), z)
         return z
+
+    @staticmethod
+    def _factors_struct(pre):
+        """oracle_factors for an IncompleteLUT / IncompleteCholesky object of the product (natural row order, i.e. the
+        reference's sequential substitutions); returns (struct, keep-alive list)."""
+        n = pre.rows()
+        keep = []
+
+        def ptr(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dt)
+            keep.append(a)
+            return a.ctypes.data
+
+        f = _OracleFactors()
+        f.n = n
+        pg, ps, qg, qs = pre.permscale()
+        f.pre_gather, f.pre_scale = ptr(pg, np.int32), ptr(ps, np.float64)
+        f.post_gather, f.post_scale = ptr(qg, np.int32), ptr(qs, np.float64)
+        for w in (0, 1):
+            st = pre.stage(w)
+            f.rowptr[w], f.colidx[w], f.vals[w] = ptr(st.rowptr, np.int32), ptr(st.colidx, np.int32), ptr(st.vals, np.float64)
+            f.diag[w] = ptr(st.diag, np.float64)
+            order = np.arange(n, dtype=np.int32) if w == 0 else np.arange(n - 1, -1, -1, dtype=np.int32)
+            f.order[w] = ptr(order, np.int32)
+            f.fused[w] = int(st.fused)
+        f.work = ptr(np.zeros(max(n, 1)), np.float64)
+        return f, keep
+
+    def cg_factors(self, A, b, pre, x0=None, tol=-1.0, max_iters=-1, uplo=BOTH, lanes=None):
+        """ConjugateGradient<_, uplo, IncompleteCholesky> (or any factor preconditioner `pre` of the product)."""
+        lanes = host_lanes(np.float64) if lanes is None else lanes
+        f, keep = self._factors_struct(pre)
+        x = np.zeros(A.rows) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+        it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
+        self.lib.oracle_cg_factors_f64(A.rows, A.rowptr, A.colidx, np.ascontiguousarray(A.vals, np.float64),
+                                       np.ascontiguousarray(b, np.float64), x, tol, max_iters, uplo, lanes, C.byref(f),
+                                       C.byref(it), C.byref(err), C.byref(info))
+        return x, it.value, err.value, info.value
+
+    def bicgstab_factors(self, A, b, pre, x0=None, tol=-1.0, max_iters=-1, lanes=None):
+        """BiCGSTAB<_, IncompleteLUT> (or any factor preconditioner `pre` of the product)."""
+        lanes = host_lanes(np.float64) if lanes is None else lanes
+        f, keep = self._factors_struct(pre)
+        x = np.zeros(A.rows) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+        it, err, info = C.c_int64(0), C.c_double(0), C.c_int(0)
+        self.lib.oracle_bicgstab_factors_f64(A.rows, A.rowptr, A.colidx, np.ascontiguousarray(A.vals, np.float64),
+                                             np.ascontiguousarray(b, np.float64), x, tol, max_iters, lanes, C.byref(f),
+                                             C.byref(it), C.byref(err), C.byref(info))
+        return x, it.value, err.value, info.value
 
     def true_residual(self, A, x, b):
         return self.lib.oracle_true_residual_f64(A.rows, A.rowptr, A.colidx, A.vals.astype(np.float64),

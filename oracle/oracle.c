@@ -89,3 +89,44 @@ void oracle_permute_scale_f64(int64_t n, const double* in, const int32_t* gather
     out[k] = scale ? scale[k] * v : v;
   }
 }
+
+/* A preconditioner object for oracle_cg_precond_f64 / oracle_bicgstab_precond_f64: the staged form of an incomplete
+ * factorization (what eigen-git-mirror_b200/csrc/factors.cpp hands to the device), applied with the reference's natural
+ * row order -- i.e. IncompleteLUT::_solve_impl (IncompleteLUT.h:171-176) / IncompleteCholesky::_solve_impl
+ * (IncompleteCholesky.h:149-157) as restated by oracle_permute_scale_f64 + oracle_tri_stage_f64 above. */
+typedef struct {
+  int64_t n;
+  const int32_t* pre_gather;   /* NULL = identity */
+  const double* pre_scale;     /* NULL = 1 */
+  const int32_t* post_gather;
+  const double* post_scale;
+  const int32_t* rowptr[2];
+  const int32_t* colidx[2];
+  const double* vals[2];
+  const double* diag[2];       /* NULL = unit diagonal */
+  const int32_t* order[2];     /* rows in the order they are solved */
+  int32_t fused[2];
+  double* work;                /* n doubles */
+} oracle_factors;
+
+void oracle_factors_apply(void* ctx, int64_t n, const double* r, double* z) {
+  const oracle_factors* f = (const oracle_factors*)ctx;
+  oracle_permute_scale_f64(n, r, f->pre_gather, f->pre_scale, f->work);
+  for (int s = 0; s < 2; ++s)
+    oracle_tri_stage_f64(n, f->rowptr[s], f->colidx[s], f->vals[s], f->diag[s], f->order[s], f->fused[s], f->work);
+  oracle_permute_scale_f64(n, f->work, f->post_gather, f->post_scale, z);
+}
+
+/* ConjugateGradient<_, UpLo, IncompleteCholesky<...>> / BiCGSTAB<_, IncompleteLUT> with the loops of oracle_body.h */
+void oracle_cg_factors_f64(int64_t n, const int32_t* rowptr, const int32_t* colidx, const double* vals, const double* b,
+                           double* x, double tol, int64_t max_iters, int uplo, int lanes, oracle_factors* f,
+                           int64_t* iters_out, double* error_out, int* info_out) {
+  oracle_cg_precond_f64(n, rowptr, colidx, vals, b, x, tol, max_iters, uplo, lanes, oracle_factors_apply, f, iters_out,
+                        error_out, info_out);
+}
+void oracle_bicgstab_factors_f64(int64_t n, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                                 const double* b, double* x, double tol, int64_t max_iters, int lanes, oracle_factors* f,
+                                 int64_t* iters_out, double* error_out, int* info_out) {
+  oracle_bicgstab_precond_f64(n, rowptr, colidx, vals, b, x, tol, max_iters, lanes, oracle_factors_apply, f, iters_out,
+                              error_out, info_out);
+}

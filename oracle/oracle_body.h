@@ -138,25 +138,29 @@ static void NAME(apply_op)(int64_t n, const int32_t* rowptr, const int32_t* coli
     NAME(oracle_symv)(n, rowptr, colidx, vals, x, y, uplo);
 }
 
-/* ---- Jacobi / identity preconditioned conjugate gradient --------------------------------------------------------
+/* ---- preconditioner hook -----------------------------------------------------------------------------------------
+ * z = precond.solve(r) of the solver loops.  Jacobi / identity: z = invdiag .* r (BasicPreconditioners.h:88-101);
+ * incomplete factorizations: the staged triangular solves of oracle.c (oracle_factors_apply, double only). */
+typedef void (*NAME(oracle_precond_fn))(void* ctx, int64_t n, const REAL* r, REAL* z);
+static void NAME(jacobi_apply)(void* ctx, int64_t n, const REAL* r, REAL* z) {
+  const REAL* invdiag = (const REAL*)ctx;
+  for (int64_t i = 0; i < n; ++i) z[i] = invdiag[i] * r[i];
+}
+
+/* ---- preconditioned conjugate gradient --------------------------------------------------------------------------
  * IterativeLinearSolvers/ConjugateGradient.h:26-91 (loop) and :197-221 (operator view, iterations/error/info).
  * x holds the initial guess on entry (zeros for solve(), IterativeSolverBase.h:399-404).
  * max_iters < 0 -> default 2*n (IterativeSolverBase.h:281-284); tol < 0 -> epsilon (:413).
  * info: 0 Success, 2 NoConvergence (Core/util/Constants.h:430-440). */
-void NAME(oracle_cg)(int64_t n, const int32_t* rowptr, const int32_t* colidx, const REAL* vals, const REAL* b,
-                     REAL* x, REAL tol, int64_t max_iters, int uplo, int precond, int lanes, int64_t* iters_out,
-                     REAL* error_out, int* info_out) {
+void NAME(oracle_cg_precond)(int64_t n, const int32_t* rowptr, const int32_t* colidx, const REAL* vals, const REAL* b,
+                             REAL* x, REAL tol, int64_t max_iters, int uplo, int lanes, NAME(oracle_precond_fn) precond,
+                             void* ctx, int64_t* iters_out, REAL* error_out, int* info_out) {
   if (max_iters < 0) max_iters = 2 * n;
   if (tol < 0) tol = EPS;
-  REAL* invdiag = (REAL*)malloc(sizeof(REAL) * (size_t)(n ? n : 1));
   REAL* r = (REAL*)malloc(sizeof(REAL) * (size_t)(n ? n : 1));
   REAL* p = (REAL*)malloc(sizeof(REAL) * (size_t)(n ? n : 1));
   REAL* z = (REAL*)malloc(sizeof(REAL) * (size_t)(n ? n : 1));
   REAL* tmp = (REAL*)malloc(sizeof(REAL) * (size_t)(n ? n : 1));
-  if (precond == 1)
-    NAME(oracle_jacobi_factorize)(n, rowptr, colidx, vals, invdiag);
-  else
-    for (int64_t i = 0; i < n; ++i) invdiag[i] = (REAL)1;
 
   int64_t it = 0;
   REAL err;
@@ -178,7 +182,7 @@ void NAME(oracle_cg)(int64_t n, const int32_t* rowptr, const int32_t* colidx, co
       err = SQRT(rr / bb);
       goto done;
     }
-    for (int64_t i = 0; i < n; ++i) p[i] = invdiag[i] * r[i]; /* :63-64 */
+    precond(ctx, n, r, p);                                    /* :63-64 */
     REAL abs_new = NAME(oracle_dot)(r, p, n, lanes);          /* :67 */
     while (it < max_iters) {                                  /* :69 */
       NAME(apply_op)(n, rowptr, colidx, vals, uplo, p, tmp);  /* :71 */
@@ -187,7 +191,7 @@ void NAME(oracle_cg)(int64_t n, const int32_t* rowptr, const int32_t* colidx, co
       for (int64_t i = 0; i < n; ++i) r[i] = FMA(-alpha, tmp[i], r[i]); /* :75 */
       rr = NAME(oracle_dot)(r, r, n, lanes);                            /* :77 */
       if (rr < thr) break;                                              /* :78-79, `it` not incremented */
-      for (int64_t i = 0; i < n; ++i) z[i] = invdiag[i] * r[i];         /* :81 */
+      precond(ctx, n, r, z);                                            /* :81 */
       REAL abs_old = abs_new;
       abs_new = NAME(oracle_dot)(r, z, n, lanes); /* :84 */
       REAL beta = abs_new / abs_old;              /* :85 */
@@ -200,27 +204,37 @@ done:
   if (iters_out) *iters_out = it;
   if (error_out) *error_out = err;
   if (info_out) *info_out = (err <= tol) ? 0 : 2; /* :220 */
-  free(invdiag); free(r); free(p); free(z); free(tmp);
+  free(r); free(p); free(z); free(tmp);
 }
 
-/* ---- Jacobi / identity preconditioned BiCGSTAB -------------------------------------------------------------------
- * IterativeLinearSolvers/BiCGSTAB.h:28-107 (loop) and :193-204 (info).  The operator is always the matrix as
- * stored.  When ||b|| == 0 the reference returns before touching iters/tol_error, so iterations() stays
- * maxIterations() and error() stays the tolerance (:47-51 with :196-199). */
-void NAME(oracle_bicgstab)(int64_t n, const int32_t* rowptr, const int32_t* colidx, const REAL* vals, const REAL* b,
-                           REAL* x, REAL tol, int64_t max_iters, int precond, int lanes, int64_t* iters_out,
-                           REAL* error_out, int* info_out) {
-  if (max_iters < 0) max_iters = 2 * n;
-  if (tol < 0) tol = EPS;
-  size_t bytes = sizeof(REAL) * (size_t)(n ? n : 1);
-  REAL* invdiag = (REAL*)malloc(bytes);
-  REAL *r = (REAL*)malloc(bytes), *r0 = (REAL*)malloc(bytes), *v = (REAL*)calloc(n ? n : 1, sizeof(REAL));
-  REAL *p = (REAL*)calloc(n ? n : 1, sizeof(REAL)), *y = (REAL*)malloc(bytes), *z = (REAL*)malloc(bytes);
-  REAL *s = (REAL*)malloc(bytes), *t = (REAL*)malloc(bytes);
+/* Jacobi (precond 1) / identity (0): DiagonalPreconditioner / IdentityPreconditioner, BasicPreconditioners.h:64-101, :200-222 */
+void NAME(oracle_cg)(int64_t n, const int32_t* rowptr, const int32_t* colidx, const REAL* vals, const REAL* b,
+                     REAL* x, REAL tol, int64_t max_iters, int uplo, int precond, int lanes, int64_t* iters_out,
+                     REAL* error_out, int* info_out) {
+  REAL* invdiag = (REAL*)malloc(sizeof(REAL) * (size_t)(n ? n : 1));
   if (precond == 1)
     NAME(oracle_jacobi_factorize)(n, rowptr, colidx, vals, invdiag);
   else
     for (int64_t i = 0; i < n; ++i) invdiag[i] = (REAL)1;
+  NAME(oracle_cg_precond)(n, rowptr, colidx, vals, b, x, tol, max_iters, uplo, lanes, NAME(jacobi_apply), invdiag,
+                          iters_out, error_out, info_out);
+  free(invdiag);
+}
+
+/* ---- preconditioned BiCGSTAB ---------------------------------------------------------------------------------------
+ * IterativeLinearSolvers/BiCGSTAB.h:28-107 (loop) and :193-204 (info).  The operator is always the matrix as
+ * stored.  When ||b|| == 0 the reference returns before touching iters/tol_error, so iterations() stays
+ * maxIterations() and error() stays the tolerance (:47-51 with :196-199). */
+void NAME(oracle_bicgstab_precond)(int64_t n, const int32_t* rowptr, const int32_t* colidx, const REAL* vals,
+                                   const REAL* b, REAL* x, REAL tol, int64_t max_iters, int lanes,
+                                   NAME(oracle_precond_fn) precond, void* ctx, int64_t* iters_out, REAL* error_out,
+                                   int* info_out) {
+  if (max_iters < 0) max_iters = 2 * n;
+  if (tol < 0) tol = EPS;
+  size_t bytes = sizeof(REAL) * (size_t)(n ? n : 1);
+  REAL *r = (REAL*)malloc(bytes), *r0 = (REAL*)malloc(bytes), *v = (REAL*)calloc(n ? n : 1, sizeof(REAL));
+  REAL *p = (REAL*)calloc(n ? n : 1, sizeof(REAL)), *y = (REAL*)malloc(bytes), *z = (REAL*)malloc(bytes);
+  REAL *s = (REAL*)malloc(bytes), *t = (REAL*)malloc(bytes);
 
   int64_t it = max_iters;
   REAL err = tol;
@@ -253,11 +267,11 @@ void NAME(oracle_bicgstab)(int64_t n, const int32_t* rowptr, const int32_t* coli
       }
       REAL beta = (rho / rho_old) * (alpha / w); /* :82 */
       for (int64_t i = 0; i < n; ++i) p[i] = FMA(beta, FMA(-w, v[i], p[i]), r[i]); /* :83 */
-      for (int64_t i = 0; i < n; ++i) y[i] = invdiag[i] * p[i];                    /* :85 */
+      precond(ctx, n, p, y);                                                       /* :85 */
       NAME(oracle_spmv)(n, rowptr, colidx, vals, y, v);                            /* :87 */
       alpha = rho / NAME(oracle_dot)(r0, v, n, lanes);                             /* :89 */
       for (int64_t i = 0; i < n; ++i) s[i] = FMA(-alpha, v[i], r[i]);              /* :90 */
-      for (int64_t i = 0; i < n; ++i) z[i] = invdiag[i] * s[i];                    /* :92 */
+      precond(ctx, n, s, z);                                                       /* :92 */
       NAME(oracle_spmv)(n, rowptr, colidx, vals, z, t);                            /* :93 */
       REAL tt = NAME(oracle_dot)(t, t, n, lanes);                                  /* :95 */
       if (tt > (REAL)0)
@@ -279,5 +293,18 @@ done:
   if (iters_out) *iters_out = it;
   if (error_out) *error_out = err;
   if (info_out) *info_out = (err <= tol) ? 0 : 2; /* :201-203 */
-  free(invdiag); free(r); free(r0); free(v); free(p); free(y); free(z); free(s); free(t);
+  free(r); free(r0); free(v); free(p); free(y); free(z); free(s); free(t);
+}
+
+void NAME(oracle_bicgstab)(int64_t n, const int32_t* rowptr, const int32_t* colidx, const REAL* vals, const REAL* b,
+                           REAL* x, REAL tol, int64_t max_iters, int precond, int lanes, int64_t* iters_out,
+                           REAL* error_out, int* info_out) {
+  REAL* invdiag = (REAL*)malloc(sizeof(REAL) * (size_t)(n ? n : 1));
+  if (precond == 1)
+    NAME(oracle_jacobi_factorize)(n, rowptr, colidx, vals, invdiag);
+  else
+    for (int64_t i = 0; i < n; ++i) invdiag[i] = (REAL)1;
+  NAME(oracle_bicgstab_precond)(n, rowptr, colidx, vals, b, x, tol, max_iters, lanes, NAME(jacobi_apply), invdiag,
+                                iters_out, error_out, info_out);
+  free(invdiag);
 }

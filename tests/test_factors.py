@@ -311,3 +311,42 @@ def test_degenerate_sizes(ref3, port):
         assert np.array_equal(port.factors_apply(IncompleteCholesky(A, uplo=1), r), ref3.ichol_solve(A, r, 1, 0))
     E = wl.CsrMatrix(0, 0, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
     assert IncompleteLUT(E).info() == 0 and IncompleteCholesky(E, uplo=1).info() == 0
+
+
+# ------------------------------------------------------ 4. the CPU restatement of the preconditioned solver loops
+@pytest.mark.parametrize("name,A", [MATS[0], MATS[2], MATS[3], MATS[5]], ids=[IDS[0], IDS[2], IDS[3], IDS[5]])
+@pytest.mark.parametrize("uplo,ordering", [(1, 0), (1, 1), (2, 1), (3, 1)])
+def test_port_cg_with_incomplete_cholesky_is_the_references(ref_any, port, name, A, uplo, ordering):
+    """oracle_cg_precond (oracle_body.h) + the staged IncompleteCholesky apply (oracle.c) against the unmodified
+    ConjugateGradient<_, UpLo, IncompleteCholesky<double, UpLo or Lower, Natural | AMD>>: x, iterations(), error() and
+    info() bit for bit, on both ISA builds (the reduction pattern follows the build, the factor is the build's own)."""
+    lanes = 8 if ref_any.variant == "v4" else 4
+    b = np.asarray(A.to_scipy() @ wl.random_vector(A.rows, 12345))
+    cp, ri, lv, sc, perm, info = ref_any.ichol(A, 1 if uplo == 3 else uplo, ordering)
+    assert info == 0
+    pre = IncompleteCholesky.from_factors(cp, ri, lv, sc, perm)
+    for mi in (-1, 3):
+        want = ref_any.precond_solver("cg_ichol", A, b, tol=1e-10, max_iters=mi, uplo=uplo, ordering=ordering)
+        got = port.cg_factors(A, b, pre, tol=1e-10, max_iters=mi, uplo=uplo, lanes=lanes)
+        assert got[1:] == want[1:], (got[1:], want[1:])
+        assert np.array_equal(got[0], want[0])
+
+
+@pytest.mark.parametrize("name,A", [MATS[0], MATS[1], MATS[4]], ids=[IDS[0], IDS[1], IDS[4]])
+def test_port_bicgstab_with_ilut_is_the_references(ref_any, port, name, A):
+    lanes = 8 if ref_any.variant == "v4" else 4
+    b = np.asarray(A.to_scipy() @ wl.random_vector(A.rows, 12345))
+    for droptol, fill in ((-1.0, 0), (1e-2, 5)):
+        rp, ci, va, P, _, info = ref_any.ilut(A, droptol, fill)
+        pre = IncompleteLUT.from_factors(rp, ci, va, P)
+        for mi in (-1, 2):
+            want = ref_any.precond_solver("bicgstab_ilut", A, b, tol=1e-10, max_iters=mi, droptol=droptol, fillfactor=fill)
+            got = port.bicgstab_factors(A, b, pre, tol=1e-10, max_iters=mi, lanes=lanes)
+            assert (got[1], got[3]) == (want[1], want[3]), (got[1:], want[1:])
+            if A.rows % 8 == 0:
+                assert got[2] == want[2] and np.array_equal(got[0], want[0])
+            else:
+                # outside the BiCGSTAB port's pinned range (DESIGN section 2: the scalar remainder of
+                # `x += alpha*y + w*z` is contracted differently when the length is not a multiple of the packet)
+                assert abs(got[2] - want[2]) <= 1e-9 * want[2]
+                assert np.allclose(got[0], want[0], rtol=0, atol=1e-13 * np.abs(want[0]).max())

@@ -119,9 +119,11 @@ def test_preconditioned_solver_golden(case, egm):
     s.close()
 
 
-def test_incomplete_cholesky_cg_at_96_cubed(egm):
+def test_incomplete_cholesky_cg_at_96_cubed(egm, port):
     """Beyond the goldens: 3-D Poisson 96^3 (885k unknowns, 286 dependency levels), natural ordering.  IC-preconditioned
-    CG converges to the known solution in far fewer iterations than Jacobi-preconditioned CG, true residual below tol."""
+    CG converges to the known solution in far fewer iterations than Jacobi-preconditioned CG, true residual below tol;
+    iterations and x as the CPU restatement of the reference's loop gives them (oracle_cg_precond, pinned bit for bit to
+    the unmodified reference by tests/test_factors.py)."""
     from eigen_git_mirror_b200 import workloads as wl
     A = wl.poisson3d(96)
     xt = wl.random_vector(A.rows, 12345)
@@ -133,6 +135,9 @@ def test_incomplete_cholesky_cg_at_96_cubed(egm):
     assert s.info() == egm.Success and pre.info() == egm.Success
     assert np.linalg.norm(A.to_scipy() @ x - b) <= 2e-10 * np.linalg.norm(b)
     assert np.linalg.norm(x - xt) <= 1e-7 * np.linalg.norm(xt)
+    xr, itr, errr, infor = port.cg_factors(A, b, pre, tol=1e-10)
+    assert infor == 0 and abs(s.iterations() - itr) <= max(1, 0.02 * itr), (s.iterations(), itr)
+    assert np.linalg.norm(x - xr) <= (1e-8 if s.iterations() == itr else 1e-7) * np.linalg.norm(xr)
     j = egm.ConjugateGradient(A)
     j.setTolerance(1e-10)
     j.solve(b)
@@ -150,16 +155,20 @@ def test_incomplete_cholesky_cg_at_96_cubed(egm):
     j.close()
 
 
-def test_ilut_bicgstab_on_convection_diffusion_64_cubed(egm):
+def test_ilut_bicgstab_on_convection_diffusion_64_cubed(egm, port):
     from eigen_git_mirror_b200 import workloads as wl
     A = wl.convdiff3d(64)
     xt = wl.random_vector(A.rows, 12345)
     b = np.asarray(A.to_scipy() @ xt)
-    s = egm.BiCGSTAB(A, preconditioner=egm.IncompleteLUT(droptol=1e-3, fillfactor=4))
+    pre = egm.IncompleteLUT(droptol=1e-3, fillfactor=4)
+    s = egm.BiCGSTAB(A, preconditioner=pre)
     s.setTolerance(1e-10)
     x = s.solve(b)
     assert s.info() == egm.Success
     assert np.linalg.norm(A.to_scipy() @ x - b) <= 2e-10 * np.linalg.norm(b)
+    xr, itr, errr, infor = port.bicgstab_factors(A, b, pre, tol=1e-10)   # the reference's loop, restated on the CPU
+    assert infor == 0 and abs(s.iterations() - itr) <= 1, (s.iterations(), itr)
+    assert np.linalg.norm(x - xr) <= (1e-8 if s.iterations() == itr else 1e-7) * np.linalg.norm(xr)
     j = egm.BiCGSTAB(A)
     j.setTolerance(1e-10)
     j.solve(b)
