@@ -283,7 +283,8 @@ int b200s_get_stats(b200s_handle* h, b200s_stats* out /* out->struct_size must b
 /* Copies the preconditioner's inverse diagonal (this rank's rows) to the host: DiagonalPreconditioner::m_invdiag. */
 int b200s_get_invdiag_f64(b200s_handle* h, double* invdiag);
 /* Per-iteration squared residual norms of the last solve (at most `cap`), for trajectory parity;
- * returns the number written, or a negative status. */
+ * returns the number written, or a negative status.  Recorded by the fused CG / BiCGSTAB loops (Jacobi / identity);
+ * 0 after a solve with an incomplete-factorization preconditioner. */
 int64_t b200s_get_residual_history(b200s_handle* h, double* rr, int64_t cap);
 
 /* Device-side timeline of the last solve (globaltimer, this rank): out[e] / out[12+e] = microseconds / count of the
