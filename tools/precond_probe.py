@@ -12,11 +12,13 @@ import eigen_git_mirror_b200 as egm  # noqa: E402
 from eigen_git_mirror_b200 import workloads as wl  # noqa: E402
 
 
-def run(kind, n):
+def run(kind, n, ordering="natural"):
     A = (wl.poisson3d if kind == "cg" else wl.convdiff3d)(n)
     b = np.asarray(A.to_scipy() @ wl.random_vector(A.rows, 12345))
     t0 = time.perf_counter()
-    pre = egm.IncompleteCholesky(uplo=egm.Lower) if kind == "cg" else egm.IncompleteLUT(droptol=1e-3, fillfactor=4)
+    perm = egm.multicolor_ordering(A)[0] if ordering == "multicolor" else None
+    pre = (egm.IncompleteCholesky(uplo=egm.Lower, perm=perm) if kind == "cg"
+           else egm.IncompleteLUT(droptol=1e-3, fillfactor=4, perm=perm))
     S = egm.ConjugateGradient if kind == "cg" else egm.BiCGSTAB
     s = S(A, preconditioner=pre)
     setup = time.perf_counter() - t0
@@ -25,7 +27,7 @@ def run(kind, n):
     x = s.solve(b)
     st = s.stats()
     res = float(np.linalg.norm(A.to_scipy() @ x - b) / np.linalg.norm(b))
-    out = {"solver": S.__name__, "preconditioner": type(pre).__name__, "grid": n, "rows": A.rows, "nnz": A.nnz,
+    out = {"solver": S.__name__, "preconditioner": type(pre).__name__, "ordering": ordering, "grid": n, "rows": A.rows, "nnz": A.nnz,
            "iterations": s.iterations(), "error": s.error(), "info": s.info(), "true_residual": res,
            "solve_ms": st["last_solve_ms"], "launches": st["last_kernel_launches"], "setup_s": round(setup, 2),
            "factor_nnz": int(pre.L.b200s_factors_nnz(pre.handle())),
@@ -49,4 +51,5 @@ def run(kind, n):
 
 if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [128, 64]
-    print(json.dumps({"ichol_cg": run("cg", sizes[0]), "ilut_bicgstab": run("bicg", sizes[1])}))
+    print(json.dumps({"ichol_cg": run("cg", sizes[0]), "ichol_cg_multicolor": run("cg", sizes[0], "multicolor"),
+                      "ilut_bicgstab": run("bicg", sizes[1])}))
